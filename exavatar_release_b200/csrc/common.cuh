@@ -1,0 +1,182 @@
+// common.cuh -- shared constants, buffer layouts and device helpers of the B200 rasteriser.
+// Algorithm constants follow SURVEY.md App. A (the published 3DGS rasteriser the reference imports at
+// avatar/common/nets/module.py:11); the kernel design is this repository's own.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/b200raster.h"
+
+namespace b2r {
+
+constexpr int TILE = 16;           // pixels per tile edge (App. A constants)
+constexpr int TILE_PIX = TILE * TILE;
+constexpr float K_NEAR = 0.2f;
+constexpr float K_DILATE = 0.3f;
+constexpr float K_ALPHA_MAX = 0.99f;
+constexpr float K_ALPHA_MIN = 1.0f / 255.0f;
+constexpr float K_T_MIN = 0.0001f;
+constexpr float K_FRUSTUM = 1.3f;
+constexpr float K_EPS_W = 0.0000001f;
+constexpr float K_EIG_FLOOR = 0.1f;
+constexpr float LOG2E = 1.4426950408889634f;
+constexpr float INV_LOG2E = 0.6931471805599453f;
+// slack (in log2 units) added to the "can this splat reach alpha >= 1/255 anywhere in this pixel rect" test so
+// that rounding in the per-pixel evaluation can never disagree with a cull decision
+constexpr float CULL_MARGIN2 = 0.02f;
+
+constexpr size_t ALIGN = 256;
+__host__ __device__ inline size_t align_up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
+
+struct Geom {  // 48 bytes per Gaussian, three 16-byte vectors
+  float4 g0;   // px, py, A2, B2
+  float4 g1;   // C2, opacity, depth, thr2
+  float4 g2;   // r, g, b, bits (SH clamp mask in bits 0..2)
+};
+static_assert(sizeof(Geom) == 48, "Geom must be 48 bytes");
+
+struct CtxLayout {
+  size_t status, geom, aux, ranges, tile_count, tile_cursor, final_T, n_contrib, total;
+  int gx, gy, tiles;
+};
+__host__ __device__ inline CtxLayout ctx_layout(int P, int W, int H) {
+  CtxLayout L;
+  L.gx = (W + TILE - 1) / TILE;
+  L.gy = (H + TILE - 1) / TILE;
+  L.tiles = L.gx * L.gy;
+  size_t Pn = P > 0 ? (size_t)P : 1, N = (size_t)W * H;
+  size_t o = 0;
+  L.status = o; o += align_up(sizeof(B2RStatus));
+  L.geom = o; o += align_up(Pn * sizeof(Geom));
+  L.aux = o; o += align_up(Pn * 16);
+  L.ranges = o; o += align_up((size_t)L.tiles * 8);
+  L.tile_count = o; o += align_up((size_t)L.tiles * 4);
+  L.tile_cursor = o; o += align_up((size_t)L.tiles * 4);
+  L.final_T = o; o += align_up(N * 4);
+  L.n_contrib = o; o += align_up(N * 4);
+  L.total = o;
+  return L;
+}
+
+struct ScratchLayout {
+  size_t keys, total;
+};
+__host__ __device__ inline ScratchLayout scratch_layout(int P, int W, int H, uint64_t cap) {
+  (void)P; (void)W; (void)H;
+  ScratchLayout S;
+  size_t o = 0;
+  S.keys = o; o += align_up((size_t)(cap > 0 ? cap : 1) * 8);
+  S.total = o;
+  return S;
+}
+
+// Resolved device pointers of one context.
+struct Ctx {
+  B2RStatus* status;
+  Geom* geom;
+  int4* aux;
+  uint2* ranges;
+  float* final_T;
+  uint32_t* n_contrib;
+  uint32_t* dup_ids;
+  uint64_t dup_capacity;
+  uint32_t* tile_count;
+  uint32_t* tile_cursor;
+  uint2* keys;
+  uint64_t* status_mirror;
+  uint64_t status_token;
+  int gx, gy, tiles;
+};
+
+inline Ctx resolve(const B2RWorkspace* ws, int P, int W, int H) {
+  CtxLayout L = ctx_layout(P, W, H);
+  ScratchLayout S = scratch_layout(P, W, H, ws->dup_capacity);
+  char* c = (char*)ws->ctx;
+  char* s = (char*)ws->scratch;
+  Ctx x;
+  x.status = (B2RStatus*)(c + L.status);
+  x.geom = (Geom*)(c + L.geom);
+  x.aux = (int4*)(c + L.aux);
+  x.ranges = (uint2*)(c + L.ranges);
+  x.final_T = (float*)(c + L.final_T);
+  x.n_contrib = (uint32_t*)(c + L.n_contrib);
+  x.dup_ids = ws->dup_ids;
+  x.dup_capacity = ws->dup_capacity;
+  x.tile_count = (uint32_t*)(c + L.tile_count);
+  x.tile_cursor = (uint32_t*)(c + L.tile_cursor);
+  x.keys = s ? (uint2*)(s + S.keys) : nullptr;
+  x.status_mirror = ws->status_mirror;
+  x.status_token = ws->status_token;
+  x.gx = L.gx; x.gy = L.gy; x.tiles = L.tiles;
+  return x;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Region test shared by the binning (16x16 tile) and the composites (8x4 warp sub-tile).
+// The splat's exponent in log2 units is  p2(dx,dy) = A2 dx^2 + B2 dx dy + C2 dy^2  with d = centre - pixel,
+// concave when A2 < 0, C2 < 0, 4 A2 C2 > B2^2.  Returns an upper bound of p2 over all pixel centres of the
+// inclusive rect [x0,x1] x [y0,y1]: exact maximum over the continuous rect (a superset of the pixel centres).
+// A splat can pass the alpha >= 1/255 test somewhere in the rect only if  bound >= thr2 (geom.g1.w).
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float region_max_p2(float sx, float sy, float A2, float B2, float C2, float x0, float y0,
+                                               float x1, float y1) {
+  const float lx = sx - x1, hx = sx - x0;  // dx range
+  const float ly = sy - y1, hy = sy - y0;  // dy range
+  const bool in_x = (lx <= 0.f) && (hx >= 0.f);
+  const bool in_y = (ly <= 0.f) && (hy >= 0.f);
+  if (in_x && in_y) return 0.f;
+  float best = -INFINITY;
+  if (!in_x) {  // nearest vertical edge; maximise over dy on it
+    const float ex = lx > 0.f ? lx : hx;
+    float dy = __fdividef(-B2 * ex, 2.f * C2);
+    dy = fminf(fmaxf(dy, ly), hy);
+    best = fmaxf(best, A2 * ex * ex + B2 * ex * dy + C2 * dy * dy);
+  }
+  if (!in_y) {
+    const float ey = ly > 0.f ? ly : hy;
+    float dx = __fdividef(-B2 * ey, 2.f * A2);
+    dx = fminf(fmaxf(dx, lx), hx);
+    best = fmaxf(best, A2 * dx * dx + B2 * dx * ey + C2 * ey * ey);
+  }
+  return best;
+}
+
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gmem_src) {
+  unsigned s = (unsigned)__cvta_generic_to_shared(smem_dst);
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(s), "l"(gmem_src));
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;\n" ::); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;\n" ::"n"(N)); }
+
+// 16-byte vector reduction to global memory (sm_90+): one L2 atomic transaction instead of four.
+__device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
+  asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+// launch wrappers (one per translation unit)
+int launch_project(const B2RScene& sc, const Ctx& cx, int32_t* radii, cudaStream_t st);
+int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t st);
+void launch_tile_scan(const Ctx& cx, cudaStream_t st);
+int launch_composite_fwd(const B2RScene& sc, const Ctx& cx, const B2RForwardOutputs& out, cudaStream_t st);
+int launch_composite_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, float* gacc, cudaStream_t st);
+int launch_project_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, const float* gacc, cudaStream_t st);
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t st);
+
+extern int g_last_cuda_error;
+inline int check_launch() {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) {
+    g_last_cuda_error = (int)e;
+    return B2R_E_CUDA;
+  }
+  return B2R_OK;
+}
+
+}  // namespace b2r

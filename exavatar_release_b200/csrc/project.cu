@@ -1,0 +1,238 @@
+// project.cu -- K1: per-Gaussian projection + exact tile counting, and the tile-offset scan.
+//
+// Replaces, for ExAvatar's render path (avatar/common/nets/module.py:632-640), the reference rasteriser's
+// preprocess kernel, its CUB inclusive scan over Gaussians and the device->host copy of the duplicate count
+// (algorithm App. A.1).  Design differences from that pipeline:
+//   * one 48-byte packed record per Gaussian (three 16-byte vectors) instead of five SoA arrays, so the
+//     composites gather a splat with three vector loads from one 64-byte-aligned neighbourhood;
+//   * the conic is stored pre-scaled for exp2 (one MUFU.EX2, no multiply in the inner loop);
+//   * tiles are counted per TILE (histogram with L2 reductions), not per Gaussian, so the later scatter writes each
+//     tile's list contiguously and the sort is a per-tile shared-memory sort instead of a global 64-bit radix sort;
+//   * a (splat, tile) pair is dropped when the splat provably cannot reach alpha >= 1/255 at any pixel centre of
+//     the tile -- output-preserving (every dropped pair would have been skipped per pixel by App. A.3) and cuts
+//     list length for anisotropic / low-opacity splats.
+#include "gaussian_math.cuh"
+
+namespace b2r {
+
+int g_last_cuda_error = 0;
+
+__device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh, const float3 mean, const Cam& cam,
+                                          float* rgb, uint32_t& clamp_bits) {
+  float dx = mean.x - cam.campos[0], dy = mean.y - cam.campos[1], dz = mean.z - cam.campos[2];
+  const float n = sqrtf(dx * dx + dy * dy + dz * dz);
+  const float x = dx / n, y = dy / n, z = dz / n;
+  clamp_bits = 0;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    auto SH = [&](int k) { return __ldg(sh + k * 3 + c); };
+    float r = B2R_SH_C0 * SH(0);
+    if (deg > 0) {
+      r = r - B2R_SH_C1 * y * SH(1) + B2R_SH_C1 * z * SH(2) - B2R_SH_C1 * x * SH(3);
+      if (deg > 1) {
+        const float xx = x * x, yy = y * y, zz = z * z, xy = x * y, yz = y * z, xz = x * z;
+        r = r + c_SH_C2[0] * xy * SH(4) + c_SH_C2[1] * yz * SH(5) + c_SH_C2[2] * (2.f * zz - xx - yy) * SH(6) +
+            c_SH_C2[3] * xz * SH(7) + c_SH_C2[4] * (xx - yy) * SH(8);
+        if (deg > 2) {
+          r = r + c_SH_C3[0] * y * (3.f * xx - yy) * SH(9) + c_SH_C3[1] * xy * z * SH(10) +
+              c_SH_C3[2] * y * (4.f * zz - xx - yy) * SH(11) + c_SH_C3[3] * z * (2.f * zz - 3.f * xx - 3.f * yy) * SH(12) +
+              c_SH_C3[4] * x * (4.f * zz - xx - yy) * SH(13) + c_SH_C3[5] * z * (xx - yy) * SH(14) +
+              c_SH_C3[6] * x * (xx - 3.f * yy) * SH(15);
+        }
+      }
+    }
+    r += 0.5f;
+    if (r < 0.f) clamp_bits |= 1u << c;
+    rgb[c] = fmaxf(r, 0.f);
+  }
+}
+
+__global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const Ctx cx, int32_t* __restrict__ radii) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const Cam cam = load_cam(sc);
+  bool visible = false;
+  Geom g;
+  g.g0 = make_float4(0.f, 0.f, 0.f, 0.f);
+  g.g1 = make_float4(0.f, 0.f, 0.f, INFINITY);
+  g.g2 = make_float4(0.f, 0.f, 0.f, 0.f);
+  int4 aux = make_int4(0, 0, 0, 0);
+  if (i < sc.P) {
+    const float3 p = make_float3(__ldg(sc.means3D + 3 * (size_t)i), __ldg(sc.means3D + 3 * (size_t)i + 1),
+                                 __ldg(sc.means3D + 3 * (size_t)i + 2));
+    const float3 pv = xform4x3(p, cam.v);
+    if (pv.z > K_NEAR) {  // App. A.1 step 1
+      const float4 ph = xform4x4(p, cam.p);
+      const float pw = 1.f / (ph.w + K_EPS_W);
+      float c6[6];
+      if (sc.cov3D_precomp) {
+#pragma unroll
+        for (int k = 0; k < 6; k++) c6[k] = __ldg(sc.cov3D_precomp + 6 * (size_t)i + k);
+      } else {
+        const float3 s = make_float3(__ldg(sc.scales + 3 * (size_t)i), __ldg(sc.scales + 3 * (size_t)i + 1),
+                                     __ldg(sc.scales + 3 * (size_t)i + 2));
+        const float* qp = sc.rotations + 4 * (size_t)i;  // scalar loads: the tensor may be a 4-byte-aligned view
+        const float4 q = make_float4(__ldg(qp), __ldg(qp + 1), __ldg(qp + 2), __ldg(qp + 3));
+        cov3d_from_scale_rot(s, sc.scale_modifier, q, c6);
+      }
+      Ewa e;
+      ewa_project(pv, c6, cam, e);
+      const float det = e.a * e.c - e.b * e.b;
+      if (det != 0.f) {  // step 5
+        const float det_inv = 1.f / det;
+        const float conx = e.c * det_inv, cony = -e.b * det_inv, conz = e.a * det_inv;
+        const float mid = 0.5f * (e.a + e.c);
+        const float root = sqrtf(fmaxf(K_EIG_FLOOR, mid * mid - det));
+        const float lam = fmaxf(mid + root, mid - root);
+        const int radius = (int)ceilf(3.f * sqrtf(lam));
+        const float px = ((ph.x * pw + 1.f) * (float)cam.W - 1.f) * 0.5f;
+        const float py = ((ph.y * pw + 1.f) * (float)cam.H - 1.f) * 0.5f;
+        int x0 = (int)((px - (float)radius) / (float)TILE), y0 = (int)((py - (float)radius) / (float)TILE);
+        int x1 = (int)((px + (float)radius + (float)(TILE - 1)) / (float)TILE);
+        int y1 = (int)((py + (float)radius + (float)(TILE - 1)) / (float)TILE);
+        x0 = min(cx.gx, max(0, x0)); y0 = min(cx.gy, max(0, y0));
+        x1 = min(cx.gx, max(0, x1)); y1 = min(cx.gy, max(0, y1));
+        if ((x1 - x0) * (y1 - y0) != 0) {  // step 8
+          visible = true;
+          const float o = __ldg(sc.opacities + i);
+          float rgb[3];
+          uint32_t bits = 0;
+          if (sc.shs) {
+            sh_to_rgb(sc.sh_degree, sc.shs + (size_t)i * sc.sh_coeffs * 3, p, cam, rgb, bits);
+          } else {
+            rgb[0] = __ldg(sc.colors_precomp + 3 * (size_t)i);
+            rgb[1] = __ldg(sc.colors_precomp + 3 * (size_t)i + 1);
+            rgb[2] = __ldg(sc.colors_precomp + 3 * (size_t)i + 2);
+          }
+          const float A2 = -0.5f * LOG2E * conx, B2 = -LOG2E * cony, C2 = -0.5f * LOG2E * conz;
+          // thr2: smallest log2-exponent at which opacity * 2^p2 can still reach 1/255
+          float thr2;
+          const bool concave = (A2 < 0.f) && (C2 < 0.f) && (4.f * A2 * C2 > B2 * B2) && (det > 0.f);
+          if (!(o > 0.f)) thr2 = INFINITY;            // alpha <= 0 < 1/255 everywhere
+          else if (!concave) thr2 = -INFINITY;        // degenerate conic: never cull, evaluate per pixel
+          else thr2 = -log2f(255.f * o) - CULL_MARGIN2;
+          g.g0 = make_float4(px, py, A2, B2);
+          g.g1 = make_float4(C2, o, pv.z, thr2);
+          g.g2 = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float(bits));
+          // count tiles (with exact culling unless disabled)
+          const bool no_cull = (sc.flags & B2R_FLAG_NO_TILE_CULL) != 0;
+          int kept = 0;
+          for (int ty = y0; ty < y1; ty++)
+            for (int tx = x0; tx < x1; tx++) {
+              bool keep = true;
+              if (!no_cull) {
+                const float rx0 = (float)(tx * TILE), ry0 = (float)(ty * TILE);
+                const float rx1 = fminf(rx0 + (float)(TILE - 1), (float)(cam.W - 1));
+                const float ry1 = fminf(ry0 + (float)(TILE - 1), (float)(cam.H - 1));
+                keep = !(region_max_p2(px, py, A2, B2, C2, rx0, ry0, rx1, ry1) < thr2);
+              }
+              if (keep) {
+                atomicAdd(cx.tile_count + ty * cx.gx + tx, 1u);
+                kept++;
+              }
+            }
+          aux = make_int4(x0 | (y0 << 16), x1 | (y1 << 16), radius, kept);
+        }
+      }
+    }
+    radii[i] = aux.z;
+    float4* gp = reinterpret_cast<float4*>(cx.geom + i);
+    gp[0] = g.g0;
+    gp[1] = g.g1;
+    gp[2] = g.g2;
+    cx.aux[i] = aux;
+  }
+  const unsigned vis = __ballot_sync(0xffffffffu, visible);
+  if ((threadIdx.x & 31) == 0 && vis) atomicAdd(&cx.status->num_visible, (uint32_t)__popc(vis));
+}
+
+// Exclusive scan of the per-tile counts (one block; tiles <= a few 10^4).  Writes ranges[t] = [start, end) clamped to
+// the duplicate capacity, primes the scatter cursors with `start`, and publishes the total.
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx) {
+  __shared__ uint64_t warp_sums[32];
+  __shared__ uint64_t carry_s;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (threadIdx.x == 0) carry_s = 0;
+  __syncthreads();
+  for (int base = 0; base < cx.tiles; base += 1024) {
+    const int t = base + threadIdx.x;
+    const uint64_t v = t < cx.tiles ? cx.tile_count[t] : 0;
+    uint64_t inc = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+      const uint64_t n = __shfl_up_sync(0xffffffffu, inc, d);
+      if (lane >= d) inc += n;
+    }
+    if (lane == 31) warp_sums[warp] = inc;
+    __syncthreads();
+    if (warp == 0) {
+      uint64_t w = warp_sums[lane];
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint64_t n = __shfl_up_sync(0xffffffffu, w, d);
+        if (lane >= d) w += n;
+      }
+      warp_sums[lane] = w;
+    }
+    __syncthreads();
+    const uint64_t carry = carry_s;
+    const uint64_t excl = carry + (warp > 0 ? warp_sums[warp - 1] : 0) + inc - v;
+    if (t < cx.tiles) {
+      const uint64_t cap = cx.dup_capacity;
+      const uint32_t s = (uint32_t)(excl < cap ? excl : cap);
+      const uint32_t e = (uint32_t)(excl + v < cap ? excl + v : cap);
+      cx.ranges[t] = make_uint2(s, e);
+      cx.tile_cursor[t] = s;
+    }
+    __syncthreads();
+    if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) {
+    const uint64_t total = carry_s;
+    cx.status->num_dups = total;
+    cx.status->dup_capacity = cx.dup_capacity;
+    cx.status->overflow = total > cx.dup_capacity ? 1u : 0u;
+    cx.status->token = cx.status_token;
+    if (cx.status_mirror) {
+      volatile uint64_t* m = cx.status_mirror;
+      m[0] = total;
+      __threadfence_system();
+      m[1] = cx.status_token;
+    }
+  }
+}
+
+__global__ void status_reset_kernel(const Ctx cx) {
+  B2RStatus* s = cx.status;
+  s->num_dups = 0;
+  s->overflow = 0;
+  s->num_visible = 0;
+  s->consumed_fwd = 0;
+  s->consumed_bwd = 0;
+}
+
+__global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
+                                    uint8_t* __restrict__ present) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= P) return;
+  const float x = means3D[3 * (size_t)i], y = means3D[3 * (size_t)i + 1], z = means3D[3 * (size_t)i + 2];
+  const float vz = view[2] * x + view[6] * y + view[10] * z + view[14];
+  present[i] = vz > K_NEAR ? 1 : 0;
+}
+
+int launch_project(const B2RScene& sc, const Ctx& cx, int32_t* radii, cudaStream_t st) {
+  cudaMemsetAsync(cx.tile_count, 0, (size_t)cx.tiles * 4, st);
+  status_reset_kernel<<<1, 1, 0, st>>>(cx);
+  if (sc.P > 0) project_kernel<<<(sc.P + 255) / 256, 256, 0, st>>>(sc, cx, radii);
+  tile_scan_kernel<<<1, 1024, 0, st>>>(cx);
+  return check_launch();
+}
+
+void launch_tile_scan(const Ctx& cx, cudaStream_t st) { tile_scan_kernel<<<1, 1024, 0, st>>>(cx); }
+
+int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t st) {
+  if (P > 0) mark_visible_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, view, present);
+  return check_launch();
+}
+
+}  // namespace b2r

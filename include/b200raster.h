@@ -1,0 +1,158 @@
+/*
+ * b200raster.h -- C ABI of the B200-native differentiable 3D-Gaussian rasteriser.
+ *
+ * Drop-in boundary for the one hot path of mks0601/ExAvatar_RELEASE: the rasteriser that
+ * `GaussianRenderer.forward` reaches through `GaussianRasterizer(raster_settings)(...)`
+ * (avatar/common/nets/module.py:609-640).  The reference binds that path through a third-party
+ * pybind module (`diff_gaussian_rasterization_depth._C`, module.py:11, not vendored); the entry
+ * points below are what that binding would call instead:
+ *
+ *   reference interface (file:line / upstream symbol)                    replaced by
+ *   ------------------------------------------------------------------   -------------------------
+ *   _C.rasterize_gaussians(...)        <- module.py:632-640 forward      b2r_forward_project +
+ *                                                                        b2r_forward_render (or b2r_forward)
+ *   _C.rasterize_gaussians_backward(.) <- loss.backward(), train.py:46   b2r_backward
+ *   _C.mark_visible(...)               <- GaussianRasterizer.markVisible b2r_mark_visible
+ *   geom/binning/img byte arenas owned by the autograd ctx               B2RWorkspace (caller-owned)
+ *
+ * Rules of the boundary: plain pointers and sizes only (no torch / STL types); every pointer is a
+ * DEVICE pointer unless its comment says host; the library never allocates device memory, never
+ * synchronises the stream and never throws -- it returns 0 or a negative B2R_E_* code.  All work is
+ * enqueued on the caller's `stream` (a cudaStream_t passed as void*).
+ *
+ * Matrix layout (what ExAvatar hands over, module.py:605-607): `viewmatrix` / `projmatrix` are 16
+ * floats with element (r,c) of the mathematical matrix at [4*c + r].
+ */
+#ifndef B200RASTER_H_
+#define B200RASTER_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define B2R_ABI_VERSION 1
+
+#define B2R_OK 0
+#define B2R_E_INVALID (-1)      /* bad argument (null pointer, negative size, both / neither colour source ...) */
+#define B2R_E_WORKSPACE (-2)    /* ctx / scratch buffer smaller than b2r_*_bytes() reports */
+#define B2R_E_CUDA (-3)         /* a CUDA launch failed; b2r_last_cuda_error() has the cudaError_t */
+#define B2R_E_DUP_OVERFLOW (-4) /* only ever reported through B2RStatus.overflow (device side) */
+
+/* flags */
+#define B2R_FLAG_NO_TILE_CULL 1u /* keep every tile of the 3-sigma rect (reference list membership, for list parity tests) */
+#define B2R_FLAG_DEBUG 2u        /* reference `debug=True` (module.py:621): the host wrapper syncs and checks after the call */
+
+/* Scene description shared by forward and backward: the fields of GaussianRasterizationSettings
+ * (module.py:609-622) plus the per-Gaussian inputs of the call (module.py:632-640). */
+typedef struct B2RScene {
+  int32_t P;              /* number of Gaussians */
+  int32_t width, height;  /* image_width, image_height */
+  int32_t sh_degree;      /* active SH degree (0..3); ignored when colors_precomp != NULL */
+  int32_t sh_coeffs;      /* M: coefficients per Gaussian in `shs` (0 when shs == NULL) */
+  uint32_t flags;         /* B2R_FLAG_* */
+  float scale_modifier;
+  float tanfovx, tanfovy;
+  const float* bg;            /* (3) */
+  const float* viewmatrix;    /* (16) world->view, [4c+r] */
+  const float* projmatrix;    /* (16) full projection (proj*view), [4c+r] */
+  const float* campos;        /* (3) */
+  const float* means3D;       /* (P,3) */
+  const float* shs;           /* (P,M,3) or NULL */
+  const float* colors_precomp;/* (P,3) or NULL  (exactly one of shs / colors_precomp) */
+  const float* opacities;     /* (P) */
+  const float* scales;        /* (P,3) or NULL */
+  const float* rotations;     /* (P,4) (r,x,y,z), used un-normalised, or NULL */
+  const float* cov3D_precomp; /* (P,6) or NULL  (exactly one of scales+rotations / cov3D_precomp) */
+} B2RScene;
+
+/* Device-side status block; lives at offset 0 of the ctx buffer (read it back with a 64-byte D2H copy). */
+typedef struct B2RStatus {
+  uint64_t num_dups;      /* (tile, Gaussian) pairs the binning wants to emit */
+  uint64_t dup_capacity;  /* capacity the render phase ran with */
+  uint32_t overflow;      /* 1 if num_dups > dup_capacity: outputs are truncated, re-run with more room */
+  uint32_t num_visible;   /* Gaussians with radii > 0 */
+  uint64_t consumed_fwd;  /* list entries staged by the forward composite (C_f of the roofline model) */
+  uint64_t consumed_bwd;  /* list entries staged by the backward composite (C_b) */
+  uint64_t token;         /* B2RWorkspace.status_token of the project phase that filled this block */
+  uint64_t reserved[1];
+} B2RStatus;
+
+/* Caller-owned memory for one forward->backward context. */
+typedef struct B2RWorkspace {
+  void* ctx;             /* >= b2r_ctx_bytes(P,W,H); saved until backward */
+  size_t ctx_bytes;
+  uint32_t* dup_ids;     /* dup_capacity sorted per-tile Gaussian ids; saved until backward */
+  uint64_t dup_capacity;
+  void* scratch;         /* >= b2r_scratch_bytes(P,W,H,dup_capacity); free after the call returns + stream order */
+  size_t scratch_bytes;
+  uint64_t* status_mirror; /* optional device-accessible pointer to 2 x uint64 in pinned HOST memory: the project
+                              phase stores {num_dups, status_token} there (in that order) so the host can learn the
+                              duplicate count by polling, without a stream synchronisation */
+  uint64_t status_token;   /* caller-chosen, e.g. a call counter */
+} B2RWorkspace;
+
+typedef struct B2RForwardOutputs {
+  float* color;   /* (3,H,W) */
+  float* depth;   /* (H,W)  sum z*alpha*T, no background term */
+  float* alpha;   /* (H,W)  sum alpha*T */
+  int32_t* radii; /* (P)    3-sigma pixel radius, 0 when culled */
+} B2RForwardOutputs;
+
+typedef struct B2RBackwardArgs {
+  const float* dL_dcolor; /* (3,H,W) */
+  const float* dL_ddepth; /* (H,W) or NULL */
+  const float* dL_dalpha; /* (H,W) or NULL */
+  /* outputs; every element is written (zeros for culled Gaussians).  Any may be NULL. */
+  float* dL_dmeans3D;   /* (P,3) */
+  float* dL_dmeans2D;   /* (P,3) NDC-scaled screen gradient, z = 0 (module.py:626-629 reads its .grad) */
+  float* dL_dshs;       /* (P,M,3) */
+  float* dL_dcolors;    /* (P,3) */
+  float* dL_dopacities; /* (P) */
+  float* dL_dscales;    /* (P,3) */
+  float* dL_drotations; /* (P,4) */
+  float* dL_dcov3D;     /* (P,6) */
+} B2RBackwardArgs;
+
+int b2r_abi_version(void);
+const char* b2r_strerror(int code);
+int b2r_last_cuda_error(void);
+/* sizeof() of the ABI structs, for bindings to verify their mirror: 0 B2RScene, 1 B2RStatus, 2 B2RWorkspace,
+ * 3 B2RForwardOutputs, 4 B2RBackwardArgs; 0 for anything else. */
+size_t b2r_sizeof(int which);
+
+size_t b2r_ctx_bytes(int32_t P, int32_t width, int32_t height);
+size_t b2r_scratch_bytes(int32_t P, int32_t width, int32_t height, uint64_t dup_capacity);
+size_t b2r_backward_scratch_bytes(int32_t P);
+
+/* Phase A: projection, tile counting, tile scan.  Writes radii and B2RStatus.num_dups. */
+int b2r_forward_project(const B2RScene* scene, const B2RWorkspace* ws, int32_t* radii, void* stream);
+/* Phase B: duplicate-with-keys, per-tile sort, forward composite (needs phase A on the same ws). */
+int b2r_forward_render(const B2RScene* scene, const B2RWorkspace* ws, const B2RForwardOutputs* out, void* stream);
+/* Both phases with a capacity chosen up front. */
+int b2r_forward(const B2RScene* scene, const B2RWorkspace* ws, const B2RForwardOutputs* out, void* stream);
+
+/* Backward composite + backward projection.  `ws` is the forward's; `bwd_scratch` >= b2r_backward_scratch_bytes(P). */
+int b2r_backward(const B2RScene* scene, const B2RWorkspace* ws, const B2RBackwardArgs* args, void* bwd_scratch,
+                 size_t bwd_scratch_bytes, void* stream);
+
+/* present[i] = 1 iff Gaussian i passes the near-plane test (z_view > 0.2). */
+int b2r_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present, void* stream);
+
+/* Stage-level introspection for parity tests (device pointers into ctx; valid until ctx is reused).
+ * geom: P x 12 floats {px, py, A2, B2 | C2, opacity, depth, thr2 | r, g, b, bits};  A2,B2,C2 are the conic
+ * pre-scaled for exp2: A2 = -0.5*log2(e)*conic.x, B2 = -log2(e)*conic.y, C2 = -0.5*log2(e)*conic.z.
+ * aux: P x 4 int32 {rect_min (x | y<<16), rect_max (x | y<<16), radius, tiles_kept}.
+ * ranges: Tn x 2 uint32 [start,end) into dup_ids.  pixel_state: per pixel {final_T (float), n_contrib (uint32)}. */
+const float* b2r_ctx_geom(const B2RWorkspace* ws, int32_t P, int32_t width, int32_t height);
+const int32_t* b2r_ctx_aux(const B2RWorkspace* ws, int32_t P, int32_t width, int32_t height);
+const uint32_t* b2r_ctx_ranges(const B2RWorkspace* ws, int32_t P, int32_t width, int32_t height);
+const float* b2r_ctx_final_T(const B2RWorkspace* ws, int32_t P, int32_t width, int32_t height);
+const uint32_t* b2r_ctx_n_contrib(const B2RWorkspace* ws, int32_t P, int32_t width, int32_t height);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* B200RASTER_H_ */
