@@ -1,0 +1,428 @@
+#!/usr/bin/env python
+"""bench.py -- avatar train-step frames/s (forward + backward Gaussian rasterisation), BASELINE.json's metric.
+
+One "step" = every rank rasterises F frames of the workload (forward + backward, gradients of the frames summed
+into one per-rank bucket) followed, when N > 1, by ONE NCCL all-reduce of that bucket.
+Frames are independent, so ranks share nothing else: weak scaling.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--frames F] [--impl b200|reference]
+
+Legs (all in one JSON line, printed by rank 0):
+  value     device-resident: inputs already in HBM, C ABI driven through FramePlan, the step captured in a CUDA graph
+  e2e       the public plugin API (GaussianRenderer -> GaussianRasterizer autograd) with HOST buffers: pinned H2D of
+            the Gaussian attributes + target image and D2H of loss + gradients inside the timed region
+  roofline  dominant kernel's algorithmic bytes / its live CUDA-event duration (in-library profiler, second pass)
+  cpu_baseline  the CPU oracle (oracle/, "port") timed on the host cores on a bounded sample of the same workload
+`--impl reference` times that CPU oracle through the same GaussianRenderer call as the reference arm.
+
+Timing: W >= 3 warm-up steps; L2 is flushed (256 MiB memset) before every timed step, outside the per-step CUDA
+event pairs; per-rank time = sum of per-step event durations; max over ranks.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import tempfile
+import time
+
+import torch
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from exavatar_release_b200.camera import look_at_cam_param  # noqa: E402
+from exavatar_release_b200.synthetic import WORKLOADS, make_assets, make_grad_image  # noqa: E402
+
+METRIC = "avatar train-step frames/sec (fwd+bwd raster)"
+UNIT = "frames/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2", choices=[k for k in WORKLOADS if k.startswith("C")])
+    ap.add_argument("--frames", type=int, default=8, help="frames per rank per step")
+    ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU budget of the cpu_baseline leg")
+    return ap.parse_args()
+
+
+def frame_yaw(global_frame: int) -> float:
+    return -20.0 + 40.0 * ((global_frame % 8) / 7.0)  # 8 distinct cameras, yaw +-20 deg
+
+
+def config_dict(args, wl, extra=None):
+    c = {"workload": wl.name, "frames_per_rank_per_step": args.frames, "P": wl.n_avatar + wl.n_scene,
+         "image": f"{wl.width}x{wl.height}", "sh_degree": wl.sh_degree, "backward": wl.backward,
+         "parallelism": f"frames sharded over {args.gpus} rank(s), one gradient all-reduce per step" if args.gpus > 1
+         else "single GPU", "l2": "256 MiB L2 flush before every timed step (outside the event pairs)"}
+    if extra:
+        c.update(extra)
+    return c
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the CPU oracle behind the reference-facing call
+# ---------------------------------------------------------------------------------------------------------------
+def cpu_frame_fn(wl_name, seed=0):
+    """Returns a closure running one frame (fwd [+bwd]) of the workload on the CPU oracle through GaussianRenderer."""
+    from oracle import oracle as O
+    from exavatar_release_b200.renderer import GaussianRenderer, render_settings
+
+    wl = WORKLOADS[wl_name]
+    O.set_num_threads(os.cpu_count() or 1)
+    assets = make_assets(wl_name, seed=seed)
+    gi = make_grad_image(wl_name, seed)
+    renderer = GaussianRenderer(rasterizer_cls=O.OracleRasterizer, settings_cls=O.OracleSettings)
+    bg = torch.ones(3)
+    use_sh = wl.sh_degree > 0
+
+    def frame(i):
+        cam = look_at_cam_param(frame_yaw(i), (wl.height, wl.width))
+        leaves = {k: v.clone().requires_grad_(wl.backward) for k, v in assets.items()}
+        if use_sh:  # C3: colours from SH inside the rasteriser
+            st = render_settings((wl.height, wl.width), cam, bg, O.OracleSettings)._replace(sh_degree=wl.sh_degree)
+            m2 = torch.zeros(leaves["mean_3d"].shape[0], 3, requires_grad=wl.backward)
+            img = O.OracleRasterizer(st)(means3D=leaves["mean_3d"], means2D=m2, opacities=leaves["opacity"],
+                                         shs=leaves["shs"], scales=leaves["scale"], rotations=leaves["rotation"])[0]
+        else:
+            img = renderer(leaves, (wl.height, wl.width), cam, bg)["img"]
+        if wl.backward:
+            (img * gi).sum().backward()
+        return float(img.detach().sum())
+
+    return frame, O.num_threads()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    wl = WORKLOADS[args.workload]
+    frame, threads = cpu_frame_fn(args.workload)
+    # bounded sample: one frame per step
+    for i in range(args.warmup):
+        frame(i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        frame(i)
+    dt = time.perf_counter() - t0
+    fps = args.steps / dt
+    sample = f"1 frame of {wl.name} per step ({'fwd+bwd' if wl.backward else 'fwd'}), {args.steps} steps, {threads} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": config_dict(args, wl, {"frames_per_rank_per_step": 1, "parallelism": f"{threads} host threads (OpenMP)",
+                                              "l2": "n/a (CPU)"}),
+            "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
+            "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+    return 0
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# clocks
+# ---------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.proc, self.path = None, None
+        exe = shutil.which("nvidia-smi")
+        if exe is None:
+            return
+        fd, self.path = tempfile.mkstemp(suffix=".csv")
+        os.close(fd)
+        self.f = open(self.path, "w")
+        self.proc = subprocess.Popen([exe, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                      "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.f.close()
+        rows = [r.strip().split(", ") for r in open(self.path) if r.strip()]
+        os.unlink(self.path)
+        sm, reasons, mx = [], set(), None
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in rows:
+            try:
+                sm.append(float(r[0])); mx = float(r[1])
+                for n, v in zip(names, r[3:7]):
+                    if v.strip().lower().startswith("active"):
+                        reasons.add(n)
+            except Exception:
+                pass
+        if not sm:
+            return None
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ---------------------------------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch.distributed as dist
+    from exavatar_release_b200 import _lib as L
+    from exavatar_release_b200 import rasterizer as RZ
+    from exavatar_release_b200.plan import FramePlan, grad_bucket
+    from exavatar_release_b200.renderer import GaussianRenderer, render_settings
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    lib = L.load()
+    wl = WORKLOADS[args.workload]
+    F, K, Wm = args.frames, args.steps, max(args.warmup, 3)
+    P, H, Wd = wl.n_avatar + wl.n_scene, wl.height, wl.width
+    N = H * Wd
+    use_sh = wl.sh_degree > 0
+    M = (wl.sh_degree + 1) ** 2 if use_sh else 0
+    bg = torch.ones(3, device=dev)
+
+    # one Gaussian set per rank (the replicated parameters), F cameras per step
+    assets = make_assets(args.workload, seed=0, device=dev)
+    gimgs = [make_grad_image(args.workload, seed=f, device=dev) for f in range(F)]
+    cams = [look_at_cam_param(frame_yaw(rank * F + f), (H, Wd), device=dev) for f in range(F)]
+    settings = []
+    for c in cams:
+        st = render_settings((H, Wd), c, bg)
+        settings.append(st._replace(sh_degree=wl.sh_degree) if use_sh else st)
+
+    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+
+    # ---- capacity: learn the duplicate counts through the autograd front-end (exact mode) ----
+    def public_frame(f, leaves=None, grad=True):
+        lv = leaves or {k: v.detach().requires_grad_(wl.backward and grad) for k, v in assets.items()}
+        m2 = torch.zeros(P, 3, device=dev, requires_grad=wl.backward and grad)
+        rast = RZ.GaussianRasterizer(settings[f])
+        img = rast(means3D=lv["mean_3d"], means2D=m2, opacities=lv["opacity"], shs=lv["shs"] if use_sh else None,
+                   colors_precomp=None if use_sh else lv["rgb"], scales=lv["scale"], rotations=lv["rotation"])[0]
+        return img, lv, m2
+
+    dups = []
+    with torch.no_grad():
+        for f in range(F):
+            img, _, _ = public_frame(f, grad=False)
+            dups.append(RZ._state(dev).predicted[(P, Wd, H)])
+    cap = int(max(dups) * 1.1) + 4096
+
+    plan = FramePlan(P, Wd, H, cap, dev, sh_coeffs=M)
+    scenes = [plan.scene(f, settings[f], assets) for f in range(F)]
+    bucket, views = grad_bucket(P, dev, M)
+
+    def step_body():
+        for f in range(F):
+            plan.forward(scenes[f])
+            if wl.backward:
+                plan.backward(scenes[f], gimgs[f], views, accumulate=(f > 0))
+
+    graph = None
+    if not args.no_graph:
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            step_body()  # warm caches / attribute calls before capture
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        graph = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(graph):
+            step_body()
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            step_body()
+        if world > 1 and wl.backward:
+            dist.all_reduce(bucket)
+
+    def barrier():
+        torch.cuda.synchronize(dev)
+        if world > 1:
+            dist.barrier()
+
+    def timed(fn, steps, count_launches=False):
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        barrier()
+        l0 = lib.b2r_launch_count()
+        t0 = time.perf_counter()
+        for s in range(steps):
+            flush_buf.zero_()
+            ev[s][0].record()
+            fn()
+            ev[s][1].record()
+        barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), wall, lib.b2r_launch_count() - l0
+
+    # ---- leg 1: device-resident value ----
+    for _ in range(Wm):
+        step()
+    clocks = ClockSampler(local) if rank == 0 else None
+    ms_total, wall, launches_eager = timed(step, K)
+    clk = clocks.stop() if clocks else None
+    st_last = plan.status()
+    if st_last["overflow"]:
+        raise SystemExit("bench.py: duplicate capacity overflowed; results invalid")
+    kernels_per_frame = 7 + (2 if wl.backward else 0)
+    launches = launches_eager if graph is None else K * F * kernels_per_frame
+    fps = world * F * K / (ms_total * 1e-3)
+
+    # ---- leg 2: per-kernel durations (same step, eager, in-library events) ----
+    lib.b2r_profile_enable(1)
+    import ctypes as C
+    ms_arr = (C.c_double * 9)()
+    cnt_arr = (C.c_uint64 * 9)()
+    lib.b2r_profile_read(ms_arr, cnt_arr, 1)
+    cons_f, cons_b, ndups = [], [], []
+    prof_steps = min(K, 5)
+    for s in range(prof_steps):
+        flush_buf.zero_()
+        for f in range(F):
+            plan.forward(scenes[f])
+            if wl.backward:
+                plan.backward(scenes[f], gimgs[f], views, accumulate=(f > 0))
+            if s == 0:
+                stt = plan.status()
+                cons_f.append(stt["consumed_fwd"]); cons_b.append(stt["consumed_bwd"]); ndups.append(stt["num_dups"])
+    lib.b2r_profile_read(ms_arr, cnt_arr, 1)
+    lib.b2r_profile_enable(0)
+    per_kernel = {lib.b2r_kernel_name(i).decode(): {"ms_avg": (ms_arr[i] / cnt_arr[i]) if cnt_arr[i] else 0.0,
+                                                    "launches": int(cnt_arr[i])} for i in range(9)}
+    tiles = ((Wd + 15) // 16) * ((H + 15) // 16)
+    # the composites run four quarter-tile CTAs per tile, each counting what it staged: /4 = per-tile list entries
+    Cf = sum(cons_f) / len(cons_f) / 4.0
+    Cb = sum(cons_b) / len(cons_b) / 4.0 if wl.backward else 0.0
+    # algorithmic bytes per launch (SURVEY section 8d / BASELINE.md section 4)
+    algo = {"composite_fwd": 44.0 * Cf + 24.0 * N + 8.0 * tiles, "composite_bwd": 84.0 * Cb + 20.0 * N}
+    dom = max(("composite_fwd", "composite_bwd"), key=lambda k: per_kernel[k]["ms_avg"])
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ach = algo[dom] / (per_kernel[dom]["ms_avg"] * 1e-3) / 1e9 if per_kernel[dom]["ms_avg"] > 0 else 0.0
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get(dom)
+    except Exception:
+        pass
+    frame_kernel_ms = sum(v["ms_avg"] * v["launches"] for v in per_kernel.values()) / (prof_steps * F)
+    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+                "frac": ach / peak if peak else None, "traffic": traffic,
+                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
+                "algorithmic_bytes_per_launch": algo[dom], "kernel_ms_avg": per_kernel[dom]["ms_avg"],
+                "binding_bound": "instruction issue (ALU/SFU/shared memory), not HBM -- see DESIGN.md section 5",
+                "per_kernel_ms": {k: round(v["ms_avg"], 5) for k, v in per_kernel.items() if v["launches"]},
+                "sum_kernel_ms_per_frame": frame_kernel_ms,
+                "consumed_fwd_per_frame": Cf, "consumed_bwd_per_frame": Cb, "dups_per_frame": sum(ndups) / len(ndups)}
+
+    # ---- leg 3: end to end through the public API with host buffers ----
+    e2e = None
+    if not args.no_e2e:
+        host_assets = {k: v.cpu().pin_memory() for k, v in assets.items() if (k != "rgb" or not use_sh)}
+        if use_sh:
+            host_assets.pop("rgb", None)
+        host_targets = [torch.rand(3, H, Wd).pin_memory() for _ in range(F)]
+        host_grads = {k: torch.empty_like(v).pin_memory() for k, v in host_assets.items()}
+        host_m2 = torch.empty(P, 3).pin_memory()
+        host_loss = torch.empty(F).pin_memory()
+        renderer = GaussianRenderer()
+        h2d = F * (sum(v.numel() * 4 for v in host_assets.values()) + 3 * N * 4)
+        d2h = F * ((sum(v.numel() * 4 for v in host_grads.values()) + P * 12 + 4) if wl.backward else 3 * N * 4)
+        host_img = torch.empty(3, H, Wd).pin_memory()
+
+        def e2e_step():
+            for f in range(F):
+                lv = {k: v.to(dev, non_blocking=True).requires_grad_(wl.backward) for k, v in host_assets.items()}
+                tgt = host_targets[f].to(dev, non_blocking=True)
+                if use_sh:
+                    img, _, m2 = public_frame(f, leaves=lv)
+                else:
+                    o = renderer(lv, (H, Wd), cams[f], bg, raster_settings=settings[f])
+                    img, m2 = o["img"], o["mean_2d"]
+                if wl.backward:
+                    loss = (img - tgt).abs().mean()
+                    loss.backward()
+                    host_loss[f:f + 1].copy_(loss.detach().reshape(1), non_blocking=True)
+                    for k in host_grads:
+                        host_grads[k].copy_(lv[k].grad, non_blocking=True)
+                    host_m2.copy_(m2.grad, non_blocking=True)
+                else:
+                    host_img.copy_(img, non_blocking=True)
+            if world > 1 and wl.backward:
+                dist.all_reduce(bucket)  # same collective as the device-resident leg
+
+        for _ in range(3):
+            e2e_step()
+        ke = max(3, min(K, 10))
+        ms_e, _, _ = timed(e2e_step, ke)
+        e2e = {"value": world * F * ke / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "api": "GaussianRenderer.forward -> GaussianRasterizer (autograd), pinned host buffers", "steps": ke}
+
+    # ---- leg 4: CPU baseline on the host cores (rank 0) ----
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        frame, threads = cpu_frame_fn(args.workload)
+        frame(0)
+        n, t0 = 0, time.perf_counter()
+        while True:
+            frame(n); n += 1
+            if time.perf_counter() - t0 > args.cpu_seconds or n >= 64:
+                break
+        dt = time.perf_counter() - t0
+        cpu = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": f"{n} frame(s) of {wl.name} on the CPU oracle (OpenMP, {threads} threads), {dt:.1f} s"}
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
+                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                "dtype": "f32", "data": "synthetic",
+                "config": config_dict(args, wl, {"cuda_graph": graph is not None, "dup_capacity": cap,
+                                                 "frames_per_rank_per_step": F}),
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "wall_s_timed_region": wall}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        return run_reference(args)
+    return run_b200(args)
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -52,7 +52,11 @@ class B2RBackwardArgs(C.Structure):
         ("dL_dcolor", _fp), ("dL_ddepth", _fp), ("dL_dalpha", _fp),
         ("dL_dmeans3D", _fp), ("dL_dmeans2D", _fp), ("dL_dshs", _fp), ("dL_dcolors", _fp), ("dL_dopacities", _fp),
         ("dL_dscales", _fp), ("dL_drotations", _fp), ("dL_dcov3D", _fp),
+        ("flags", C.c_uint32), ("reserved", C.c_uint32),
     ]
+
+
+B2R_BWD_ACCUMULATE = 1
 
 
 # every symbol include/b200raster.h declares: (name, restype, argtypes)
@@ -70,6 +74,10 @@ SYMBOLS = [
     ("b2r_backward", C.c_int, [C.POINTER(B2RScene), C.POINTER(B2RWorkspace), C.POINTER(B2RBackwardArgs), _fp,
                                C.c_size_t, _fp]),
     ("b2r_mark_visible", C.c_int, [C.c_int32, _fp, _fp, _fp, _fp]),
+    ("b2r_profile_enable", None, [C.c_int]),
+    ("b2r_profile_read", C.c_int, [C.POINTER(C.c_double), C.POINTER(C.c_uint64), C.c_int]),
+    ("b2r_launch_count", C.c_uint64, []),
+    ("b2r_kernel_name", C.c_char_p, [C.c_int]),
     ("b2r_ctx_geom", _fp, [C.POINTER(B2RWorkspace), C.c_int32, C.c_int32, C.c_int32]),
     ("b2r_ctx_aux", _fp, [C.POINTER(B2RWorkspace), C.c_int32, C.c_int32, C.c_int32]),
     ("b2r_ctx_ranges", _fp, [C.POINTER(B2RWorkspace), C.c_int32, C.c_int32, C.c_int32]),

@@ -14,29 +14,26 @@ namespace b2r {
 
 __global__ void __launch_bounds__(256) scatter_kernel(const B2RScene sc, const Ctx cx) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= sc.P) return;
-  const int4 aux = cx.aux[i];
-  if (aux.w == 0) return;
-  const float4 g0 = reinterpret_cast<const float4*>(cx.geom + i)[0];
-  const float4 g1 = reinterpret_cast<const float4*>(cx.geom + i)[1];
-  const int x0 = aux.x & 0xffff, y0 = aux.x >> 16, x1 = aux.y & 0xffff, y1 = aux.y >> 16;
-  const bool no_cull = (sc.flags & B2R_FLAG_NO_TILE_CULL) != 0;
-  const uint32_t depth_bits = __float_as_uint(g1.z);
-  const uint64_t cap = cx.dup_capacity;
-  for (int ty = y0; ty < y1; ty++)
-    for (int tx = x0; tx < x1; tx++) {
-      bool keep = true;
-      if (!no_cull) {  // must be the same predicate as in project_kernel
-        const float rx0 = (float)(tx * TILE), ry0 = (float)(ty * TILE);
-        const float rx1 = fminf(rx0 + (float)(TILE - 1), (float)(sc.width - 1));
-        const float ry1 = fminf(ry0 + (float)(TILE - 1), (float)(sc.height - 1));
-        keep = !(region_max_p2(g0.x, g0.y, g0.z, g0.w, g1.x, rx0, ry0, rx1, ry1) < g1.w);
-      }
-      if (keep) {
-        const uint32_t pos = atomicAdd(cx.tile_cursor + ty * cx.gx + tx, 1u);
-        if (pos < cap) cx.keys[pos] = make_uint2(depth_bits, (uint32_t)i);
-      }
+  int4 aux = make_int4(0, 0, 0, 0);
+  float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+  if (i < sc.P) {
+    aux = cx.aux[i];
+    if (aux.z > 0) {
+      g0 = reinterpret_cast<const float4*>(cx.geom + i)[0];
+      g1 = reinterpret_cast<const float4*>(cx.geom + i)[1];
     }
+  }
+  const uint64_t cap = cx.dup_capacity;
+  const int gx = cx.gx;
+  uint32_t* cursor = cx.tile_cursor;
+  uint2* keys = cx.keys;
+  // same enumeration and the same predicate as the counting pass in project_kernel
+  warp_for_each_kept_tile(aux.z > 0, aux.x & 0xffff, aux.x >> 16, aux.y & 0xffff, aux.y >> 16, g0.x, g0.y, g0.z, g0.w,
+                          g1.x, g1.w, __float_as_uint(g1.z), (uint32_t)i, (sc.flags & B2R_FLAG_NO_TILE_CULL) != 0,
+                          sc.width, sc.height, [&](int tx, int ty, uint32_t depth_bits, uint32_t id) {
+                            const uint32_t pos = atomicAdd(cursor + ty * gx + tx, 1u);
+                            if (pos < cap) keys[pos] = make_uint2(depth_bits, id);
+                          });
 }
 
 // All-ascending bitonic network ("flip" then "disperse" steps).  Indices >= n behave as +inf keys, so no padding is
@@ -69,41 +66,44 @@ __device__ __forceinline__ void bitonic_sort(KeyPtr key, const int n, const int 
   }
 }
 
-// One CTA per tile; handles tiles whose list length n satisfies lo < n <= hi.  Lists longer than SMEM_CAP are sorted
-// in place in global memory by the same network (rare: > 16k splats on one tile).
+// Sorts every tile whose list length n satisfies lo < n <= hi; CTAs stride over the tiles (the small class is launched
+// with one CTA per tile, the large class with one CTA per SM so that a frame without long lists costs ~2 us).  Lists
+// longer than SMEM_CAP are sorted in place in global memory by the same network (rare: > 16k splats on one tile).
 template <int SMEM_CAP>
 __global__ void __launch_bounds__(256) sort_tiles_kernel(const Ctx cx, const int lo, const int hi) {
   extern __shared__ __align__(16) unsigned long long skeys[];
-  const int t = blockIdx.x;
-  const uint2 r = cx.ranges[t];
-  const int n = (int)(r.y - r.x);
-  if (n <= lo || n > hi) return;
-  const uint2* src = cx.keys + r.x;
-  uint32_t* dst = cx.dup_ids + r.x;
-  if (n == 1) {
-    if (threadIdx.x == 0) dst[0] = src[0].y;
-    return;
-  }
-  int npow2 = 2;
-  while (npow2 < n) npow2 <<= 1;
-  if (n <= SMEM_CAP) {
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint2 kv = src[i];
-      skeys[i] = ((unsigned long long)kv.x << 32) | kv.y;
+  for (int t = blockIdx.x; t < cx.tiles; t += gridDim.x) {
+    const uint2 r = cx.ranges[cx.tile_order[t]];  // longest lists first
+    const int n = (int)(r.y - r.x);
+    if (n <= lo || n > hi) continue;
+    const uint2* src = cx.keys + r.x;
+    uint32_t* dst = cx.dup_ids + r.x;
+    if (n == 1) {
+      if (threadIdx.x == 0) dst[0] = src[0].y;
+      continue;
     }
-    __syncthreads();
-    bitonic_sort(skeys, n, npow2);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (uint32_t)skeys[i];
-  } else {
-    // global fallback: keys are stored (depth_bits, id) = little-endian (lo, hi) words, so re-pack to depth-major first
-    unsigned long long* gk = reinterpret_cast<unsigned long long*>(cx.keys + r.x);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      const uint2 kv = src[i];
-      gk[i] = ((unsigned long long)kv.x << 32) | kv.y;
+    int npow2 = 2;
+    while (npow2 < n) npow2 <<= 1;
+    if (n <= SMEM_CAP) {
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint2 kv = src[i];
+        skeys[i] = ((unsigned long long)kv.x << 32) | kv.y;
+      }
+      __syncthreads();
+      bitonic_sort(skeys, n, npow2);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (uint32_t)skeys[i];
+      __syncthreads();  // skeys is reused by the next tile of this CTA
+    } else {
+      // global fallback: keys are stored (depth_bits, id) = little-endian (lo, hi) words, so re-pack to depth-major first
+      unsigned long long* gk = reinterpret_cast<unsigned long long*>(cx.keys + r.x);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) {
+        const uint2 kv = src[i];
+        gk[i] = ((unsigned long long)kv.x << 32) | kv.y;
+      }
+      __syncthreads();
+      bitonic_sort(gk, n, npow2);
+      for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (uint32_t)gk[i];
     }
-    __syncthreads();
-    bitonic_sort(gk, n, npow2);
-    for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (uint32_t)gk[i];
   }
 }
 
@@ -113,10 +113,20 @@ constexpr int SORT_LARGE = 16384;  // 128 KB of keys: one CTA per SM
 int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t st) {
   // the two-phase entry re-derives ranges and cursors for the capacity the caller finally chose
   if (rescan) launch_tile_scan(cx, st);
-  if (sc.P > 0) scatter_kernel<<<(sc.P + 255) / 256, 256, 0, st>>>(sc, cx);
+  if (sc.P > 0) { ProfScope p(K_SCATTER, st); scatter_kernel<<<(sc.P + 255) / 256, 256, 0, st>>>(sc, cx); }
+  static int sms = 0;
+  if (sms == 0) {
+    int dev = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    if (sms <= 0) sms = 148;
+  }
   cudaFuncSetAttribute(sort_tiles_kernel<SORT_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_LARGE * 8);
-  sort_tiles_kernel<SORT_SMALL><<<cx.tiles, 256, SORT_SMALL * 8, st>>>(cx, 0, SORT_SMALL);
-  sort_tiles_kernel<SORT_LARGE><<<cx.tiles, 256, SORT_LARGE * 8, st>>>(cx, SORT_SMALL, 0x7fffffff);
+  { ProfScope p(K_SORT_SMALL, st); sort_tiles_kernel<SORT_SMALL><<<cx.tiles, 256, SORT_SMALL * 8, st>>>(cx, 0, SORT_SMALL); }
+  {
+    ProfScope p(K_SORT_LARGE, st);
+    sort_tiles_kernel<SORT_LARGE><<<cx.tiles < sms ? cx.tiles : sms, 256, SORT_LARGE * 8, st>>>(cx, SORT_SMALL, 0x7fffffff);
+  }
   return check_launch();
 }
 

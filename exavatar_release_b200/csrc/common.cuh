@@ -36,7 +36,7 @@ struct Geom {  // 48 bytes per Gaussian, three 16-byte vectors
 static_assert(sizeof(Geom) == 48, "Geom must be 48 bytes");
 
 struct CtxLayout {
-  size_t status, geom, aux, ranges, tile_count, tile_cursor, final_T, n_contrib, total;
+  size_t status, geom, aux, ranges, tile_count, tile_cursor, tile_order, final_T, n_contrib, total;
   int gx, gy, tiles;
 };
 __host__ __device__ inline CtxLayout ctx_layout(int P, int W, int H) {
@@ -52,6 +52,7 @@ __host__ __device__ inline CtxLayout ctx_layout(int P, int W, int H) {
   L.ranges = o; o += align_up((size_t)L.tiles * 8);
   L.tile_count = o; o += align_up((size_t)L.tiles * 4);
   L.tile_cursor = o; o += align_up((size_t)L.tiles * 4);
+  L.tile_order = o; o += align_up((size_t)L.tiles * 4);
   L.final_T = o; o += align_up(N * 4);
   L.n_contrib = o; o += align_up(N * 4);
   L.total = o;
@@ -82,6 +83,7 @@ struct Ctx {
   uint64_t dup_capacity;
   uint32_t* tile_count;
   uint32_t* tile_cursor;
+  uint32_t* tile_order;  // tiles sorted longest list first (see tile_scan_kernel)
   uint2* keys;
   uint64_t* status_mirror;
   uint64_t status_token;
@@ -104,6 +106,7 @@ inline Ctx resolve(const B2RWorkspace* ws, int P, int W, int H) {
   x.dup_capacity = ws->dup_capacity;
   x.tile_count = (uint32_t*)(c + L.tile_count);
   x.tile_cursor = (uint32_t*)(c + L.tile_cursor);
+  x.tile_order = (uint32_t*)(c + L.tile_order);
   x.keys = s ? (uint2*)(s + S.keys) : nullptr;
   x.status_mirror = ws->status_mirror;
   x.status_token = ws->status_token;
@@ -141,6 +144,49 @@ __device__ __forceinline__ float region_max_p2(float sx, float sy, float A2, flo
   return best;
 }
 
+// Warp-cooperative enumeration of the tiles a Gaussian keeps (rect minus culled tiles).  Every lane brings one
+// Gaussian (or active = false).  Rects of <= 4 tiles are walked by their own lane; larger rects are broadcast and
+// walked by all 32 lanes together, so one 144-tile scene splat no longer stalls 31 idle lanes behind it.
+// f(tx, ty, u0, u1) is called once per kept tile with the owner's two payload words.  Must be called by full warps.
+template <typename F>
+__device__ __forceinline__ void warp_for_each_kept_tile(bool active, int x0, int y0, int x1, int y1, float px, float py,
+                                                        float A2, float B2, float C2, float thr2, uint32_t u0,
+                                                        uint32_t u1, bool no_cull, int W, int H, F&& f) {
+  const int lane = threadIdx.x & 31;
+  const int w = x1 - x0;
+  const int area = active ? w * (y1 - y0) : 0;
+  auto keep_tile = [&](int tx, int ty, float sx, float sy, float a2, float b2, float c2, float th) {
+    if (no_cull) return true;
+    const float rx0 = (float)(tx * TILE), ry0 = (float)(ty * TILE);
+    const float rx1 = fminf(rx0 + (float)(TILE - 1), (float)(W - 1));
+    const float ry1 = fminf(ry0 + (float)(TILE - 1), (float)(H - 1));
+    return !(region_max_p2(sx, sy, a2, b2, c2, rx0, ry0, rx1, ry1) < th);
+  };
+  constexpr int SMALL = 4;
+  if (area > 0 && area <= SMALL) {
+    for (int t = 0; t < area; t++) {
+      const int ty = y0 + t / w, tx = x0 + t - (t / w) * w;
+      if (keep_tile(tx, ty, px, py, A2, B2, C2, thr2)) f(tx, ty, u0, u1);
+    }
+  }
+  unsigned mask = __ballot_sync(0xffffffffu, area > SMALL);
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+    const int bw = __shfl_sync(0xffffffffu, w, src), barea = __shfl_sync(0xffffffffu, area, src);
+    const float spx = __shfl_sync(0xffffffffu, px, src), spy = __shfl_sync(0xffffffffu, py, src);
+    const float sA = __shfl_sync(0xffffffffu, A2, src), sB = __shfl_sync(0xffffffffu, B2, src);
+    const float sC = __shfl_sync(0xffffffffu, C2, src), sT = __shfl_sync(0xffffffffu, thr2, src);
+    const uint32_t s0 = __shfl_sync(0xffffffffu, u0, src), s1 = __shfl_sync(0xffffffffu, u1, src);
+    for (int t = lane; t < barea; t += 32) {
+      const int r = t / bw;
+      const int ty = by0 + r, tx = bx0 + t - r * bw;
+      if (keep_tile(tx, ty, spx, spy, sA, sB, sC, sT)) f(tx, ty, s0, s1);
+    }
+  }
+}
+
 __device__ __forceinline__ float ex2_approx(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
@@ -168,6 +214,18 @@ int launch_composite_fwd(const B2RScene& sc, const Ctx& cx, const B2RForwardOutp
 int launch_composite_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, float* gacc, cudaStream_t st);
 int launch_project_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, const float* gacc, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t st);
+
+// RAII bracket around one kernel launch: counts it and, when profiling is on, records CUDA events around it.
+enum KernelId { K_PROJECT = 0, K_TILE_SCAN, K_SCATTER, K_SORT_SMALL, K_SORT_LARGE, K_COMPOSITE_FWD, K_COMPOSITE_BWD,
+                K_PROJECT_BWD, K_MISC };
+struct ProfScope {
+  int id;
+  cudaStream_t st;
+  bool on;
+  cudaEvent_t a;
+  ProfScope(int id, cudaStream_t st, int launches = 1);
+  ~ProfScope();
+};
 
 extern int g_last_cuda_error;
 inline int check_launch() {

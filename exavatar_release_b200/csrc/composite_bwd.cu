@@ -1,4 +1,5 @@
-// composite_bwd.cu -- K5: backward alpha-composite (App. A.4), one CTA per 16x16 tile.
+// composite_bwd.cu -- K5: backward alpha-composite (App. A.4), one 64-thread CTA per 8x8 quarter tile, launched
+// longest-list-first (same work decomposition as composite_fwd.cu).
 //
 // Replaces the reference rasteriser's backward render kernel (reached from loss.backward(), avatar/main/train.py:46,
 // through the autograd node created at avatar/common/nets/module.py:632).  That kernel issues ~10 fp32 global atomics
@@ -17,7 +18,9 @@
 
 namespace b2r {
 
-constexpr int BWD_BATCH = 256;
+constexpr int BWD_THREADS = 64;
+constexpr int BWD_BATCH = 64;
+constexpr int BWD_PER_THREAD = BWD_BATCH / BWD_THREADS;
 
 struct BwdStage {
   float4 a[BWD_BATCH];
@@ -66,18 +69,23 @@ __device__ __forceinline__ int halving_slot(const int lane) {
 }
 
 template <bool HAS_DA>
-__global__ void __launch_bounds__(256) composite_bwd_kernel(const B2RScene sc, const Ctx cx, const B2RBackwardArgs args,
+__global__ void __launch_bounds__(BWD_THREADS) composite_bwd_kernel(const B2RScene sc, const Ctx cx, const B2RBackwardArgs args,
                                                             float* __restrict__ gacc) {
   constexpr int NV = HAS_DA ? 10 : 9;
   __shared__ BwdStage stage[2];
-  __shared__ __align__(16) float acc[BWD_BATCH][12];
-  __shared__ int warp_max_s[8];
+  // one accumulator row per (warp, staged splat): a warp visits a splat at most once per batch, so the reduced
+  // values are written with plain stores -- shared-memory fp32 atomicAdd would compile to a CAS spin loop
+  __shared__ __align__(16) float acc[2][BWD_BATCH][12];
+  __shared__ int warp_max_s[2];
+  __shared__ unsigned long long touched_s[2];  // per warp: which rows of this batch hold fresh values
 
-  const int tile = blockIdx.x;
+  const int tile = (int)cx.tile_order[blockIdx.x >> 2];
+  const int quad = blockIdx.x & 3;
   const int tx = tile % cx.gx, ty = tile / cx.gx;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int W = sc.width, H = sc.height;
-  const int wx0 = tx * TILE + (warp & 1) * 8, wy0 = ty * TILE + (warp >> 1) * 4;
+  const int wx0 = tx * TILE + (quad & 1) * 8, wy0 = ty * TILE + (quad >> 1) * 8 + warp * 4;
+  if (wx0 >= W || ty * TILE + (quad >> 1) * 8 >= H) return;  // quarter entirely outside the image (CTA-uniform)
   const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
   const bool inside = px < W && py < H;
   const float pxf = (float)px, pyf = (float)py;
@@ -103,11 +111,9 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const B2RScene sc, c
 
   const int warp_n = __reduce_max_sync(0xffffffffu, my_n);
   if (lane == 0) warp_max_s[warp] = warp_n;
-  for (int i = threadIdx.x; i < BWD_BATCH * 12; i += blockDim.x) (&acc[0][0])[i] = 0.f;
   __syncthreads();
   int nmax = 0;
-#pragma unroll
-  for (int i = 0; i < 8; i++) nmax = max(nmax, warp_max_s[i]);
+  nmax = max(warp_max_s[0], warp_max_s[1]);
   if (nmax == 0) return;
   const int nb = (nmax + BWD_BATCH - 1) / BWD_BATCH;
 
@@ -120,15 +126,19 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const B2RScene sc, c
   float acd = 0.f, lcd = 0.f, aca = 0.f;
 
   auto issue = [&](int b) {
-    const int idx = b * BWD_BATCH + threadIdx.x;
-    if (idx < nmax) {
-      const uint32_t id = __ldg(ids + idx);
-      const float4* src = reinterpret_cast<const float4*>(cx.geom + id);
-      BwdStage& s = stage[b & 1];
-      cp_async16(&s.a[threadIdx.x], src);
-      cp_async16(&s.b[threadIdx.x], src + 1);
-      cp_async16(&s.c[threadIdx.x], src + 2);
-      s.id[threadIdx.x] = id;
+    BwdStage& s = stage[b & 1];
+#pragma unroll
+    for (int u = 0; u < BWD_PER_THREAD; u++) {
+      const int slot = threadIdx.x + u * BWD_THREADS;
+      const int idx = b * BWD_BATCH + slot;
+      if (idx < nmax) {
+        const uint32_t id = __ldg(ids + idx);
+        const float4* src = reinterpret_cast<const float4*>(cx.geom + id);
+        cp_async16(&s.a[slot], src);
+        cp_async16(&s.b[slot], src + 1);
+        cp_async16(&s.c[slot], src + 2);
+        s.id[slot] = id;
+      }
     }
     cp_async_commit();
   };
@@ -140,6 +150,7 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const B2RScene sc, c
     if (b > 0) issue(b - 1);
     const int count = min(BWD_BATCH, nmax - b * BWD_BATCH);
     const BwdStage& s = stage[b & 1];
+    unsigned long long touched = 0ull;
     if (warp_n > b * BWD_BATCH) {
       for (int c0 = ((count - 1) >> 5) << 5; c0 >= 0; c0 -= 32) {
         const int idx = c0 + lane;
@@ -162,57 +173,70 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const B2RScene sc, c
           const float alpha = fminf(K_ALPHA_MAX, bb.y * G);
           const bool valid = (b * BWD_BATCH + j < my_n) && (p2 <= 0.f) && (alpha >= K_ALPHA_MIN);
           if (!__any_sync(0xffffffffu, valid)) continue;
-          float v[NV];
-#pragma unroll
-          for (int i = 0; i < NV; i++) v[i] = 0.f;
-          if (valid) {
-            const float4 col = s.c[j];
-            const float rcp = __fdividef(1.f, 1.f - alpha);
-            T *= rcp;
-            const float w = alpha * T;
-            float dLda = 0.f;
-            acr = last_alpha * lcr + (1.f - last_alpha) * acr; lcr = col.x; dLda += (col.x - acr) * g_r;
-            acg = last_alpha * lcg + (1.f - last_alpha) * acg; lcg = col.y; dLda += (col.y - acg) * g_g;
-            acb = last_alpha * lcb + (1.f - last_alpha) * acb; lcb = col.z; dLda += (col.z - acb) * g_b;
-            if (HAS_DA) {
-              acd = last_alpha * lcd + (1.f - last_alpha) * acd; lcd = bb.z; dLda += (bb.z - acd) * g_d;
-              aca = last_alpha + (1.f - last_alpha) * aca; dLda += (1.f - aca) * g_a;
-            }
-            dLda *= T;
-            last_alpha = alpha;
-            dLda += (-T_final * rcp) * bg_dot;
-            const float dLdG = bb.y * dLda;  // clamp ignored (App. A.6 i)
-            const float gdx = G * dx, gdy = G * dy;
-            v[0] = dLdG * (2.f * gdx * a.z + gdy * a.w);
-            v[1] = dLdG * (2.f * gdy * bb.x + gdx * a.w);
-            const float hx = dLdG * gdx, hy = dLdG * gdy;
-            v[2] = hx * dx;
-            v[3] = hx * dy;
-            v[4] = hy * dy;
-            v[5] = G * dLda;
-            v[6] = w * g_r;
-            v[7] = w * g_g;
-            v[8] = w * g_b;
-            if (HAS_DA) v[NV - 1] = w * g_d;
+          touched |= 1ull << j;
+          // branch-free: every lane evaluates, `valid` only selects what is kept (no divergent code in this loop)
+          const float4 col = s.c[j];
+          const float rcp = __fdividef(1.f, 1.f - alpha);
+          const float Tn = T * rcp;
+          const float w = alpha * Tn;
+          const float om = 1.f - last_alpha;
+          const float nacr = last_alpha * lcr + om * acr;
+          const float nacg = last_alpha * lcg + om * acg;
+          const float nacb = last_alpha * lcb + om * acb;
+          float dLda = (col.x - nacr) * g_r + (col.y - nacg) * g_g + (col.z - nacb) * g_b;
+          float nacd = 0.f, naca = 0.f;
+          if (HAS_DA) {
+            nacd = last_alpha * lcd + om * acd;
+            naca = last_alpha + om * aca;
+            dLda += (bb.z - nacd) * g_d + (1.f - naca) * g_a;
           }
+          dLda = dLda * Tn + (-T_final * rcp) * bg_dot;
+          const float dLdG = bb.y * dLda;  // clamp ignored (App. A.6 i)
+          const float gdx = G * dx, gdy = G * dy;
+          const float hx = dLdG * gdx, hy = dLdG * gdy;
+          float v[NV];
+          v[0] = valid ? dLdG * (2.f * gdx * a.z + gdy * a.w) : 0.f;
+          v[1] = valid ? dLdG * (2.f * gdy * bb.x + gdx * a.w) : 0.f;
+          v[2] = valid ? hx * dx : 0.f;
+          v[3] = valid ? hx * dy : 0.f;
+          v[4] = valid ? hy * dy : 0.f;
+          v[5] = valid ? G * dLda : 0.f;
+          v[6] = valid ? w * g_r : 0.f;
+          v[7] = valid ? w * g_g : 0.f;
+          v[8] = valid ? w * g_b : 0.f;
+          if (HAS_DA) v[NV - 1] = valid ? w * g_d : 0.f;
+          T = valid ? Tn : T;
+          acr = valid ? nacr : acr; lcr = valid ? col.x : lcr;
+          acg = valid ? nacg : acg; lcg = valid ? col.y : lcg;
+          acb = valid ? nacb : acb; lcb = valid ? col.z : lcb;
+          if (HAS_DA) {
+            acd = valid ? nacd : acd; lcd = valid ? bb.z : lcd;
+            aca = valid ? naca : aca;
+          }
+          last_alpha = valid ? alpha : last_alpha;
           halving_reduce<NV, 16>(v, lane);
-          if (my_col >= 0) atomicAdd(&acc[j][my_col], v[0]);
+          if (my_col >= 0) acc[warp][j][my_col] = v[0];
         }
       }
     }
+    if (lane == 0) touched_s[warp] = touched;
     __syncthreads();
-    if (threadIdx.x < count) {  // flush this batch: one row per thread
-      float4* row = reinterpret_cast<float4*>(&acc[threadIdx.x][0]);
-      const float4 q0 = row[0], q1 = row[1], q2 = row[2];
-      const bool any = (q0.x != 0.f) | (q0.y != 0.f) | (q0.z != 0.f) | (q0.w != 0.f) | (q1.x != 0.f) | (q1.y != 0.f) |
-                       (q1.z != 0.f) | (q2.x != 0.f) | (q2.y != 0.f) | (q2.z != 0.f);
-      if (any) {
-        float* dst = gacc + (size_t)s.id[threadIdx.x] * 12;
-        red_add_v4(dst, q0.x, q0.y, q0.z, q0.w);
-        red_add_v4(dst + 4, q1.x, q1.y, q1.z, 0.f);
-        red_add_v4(dst + 8, q2.x, q2.y, q2.z, 0.f);
-        const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
-        row[0] = z; row[1] = z; row[2] = z;
+#pragma unroll
+    for (int u = 0; u < BWD_PER_THREAD; u++) {  // flush this batch: one accumulator row per (thread, u)
+      const int slot = threadIdx.x + u * BWD_THREADS;
+      if (slot < count) {
+        const bool t0 = (touched_s[0] >> slot) & 1ull, t1 = (touched_s[1] >> slot) & 1ull;
+        if (t0 | t1) {
+          const float4 z = make_float4(0.f, 0.f, 0.f, 0.f);
+          const float4* row0 = reinterpret_cast<const float4*>(&acc[0][slot][0]);
+          const float4* row1 = reinterpret_cast<const float4*>(&acc[1][slot][0]);
+          const float4 p0 = t0 ? row0[0] : z, p1 = t0 ? row0[1] : z, p2 = t0 ? row0[2] : z;
+          const float4 r0 = t1 ? row1[0] : z, r1 = t1 ? row1[1] : z, r2 = t1 ? row1[2] : z;
+          float* dst = gacc + (size_t)s.id[slot] * 12;
+          red_add_v4(dst, p0.x + r0.x, p0.y + r0.y, p0.z + r0.z, p0.w + r0.w);
+          red_add_v4(dst + 4, p1.x + r1.x, p1.y + r1.y, HAS_DA ? p1.z + r1.z : 0.f, 0.f);
+          red_add_v4(dst + 8, p2.x + r2.x, p2.y + r2.y, p2.z + r2.z, 0.f);
+        }
       }
     }
   }
@@ -221,10 +245,11 @@ __global__ void __launch_bounds__(256) composite_bwd_kernel(const B2RScene sc, c
 
 int launch_composite_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, float* gacc, cudaStream_t st) {
   cudaMemsetAsync(gacc, 0, (size_t)(sc.P > 0 ? sc.P : 1) * 12 * sizeof(float), st);
+  ProfScope p(K_COMPOSITE_BWD, st);
   if (a.dL_ddepth || a.dL_dalpha)
-    composite_bwd_kernel<true><<<cx.tiles, 256, 0, st>>>(sc, cx, a, gacc);
+    composite_bwd_kernel<true><<<cx.tiles * 4, BWD_THREADS, 0, st>>>(sc, cx, a, gacc);
   else
-    composite_bwd_kernel<false><<<cx.tiles, 256, 0, st>>>(sc, cx, a, gacc);
+    composite_bwd_kernel<false><<<cx.tiles * 4, BWD_THREADS, 0, st>>>(sc, cx, a, gacc);
   return check_launch();
 }
 

@@ -1,24 +1,29 @@
-// composite_fwd.cu -- K4: forward alpha-composite (App. A.3), one CTA per 16x16 tile.
+// composite_fwd.cu -- K4: forward alpha-composite (App. A.3).
 //
 // Replaces the reference rasteriser's forward render kernel for ExAvatar's render path
 // (avatar/common/nets/module.py:632 -> render_img, render_depthmap, render_mask).
 //
-// Design (B200): the kernel is issue-bound, not HBM-bound, so the structure is built around
-// removing per-pixel work rather than around bytes:
-//   * the tile's depth-sorted id list is streamed in batches of 256; each thread gathers one 48-byte splat record
-//     (three 16-byte cp.async = LDGSTS, no register staging) into a double-buffered shared-memory stage while the
-//     previous batch is being composited;
-//   * each warp owns an 8x4 pixel sub-tile.  For every 32 staged splats the warp runs ONE lane-parallel test
-//     "can this splat reach alpha >= 1/255 anywhere in my 8x4 rect" (region_max_p2), ballots, and walks only the
-//     surviving splats with lanes = pixels.  For ExAvatar's millimetre-scale avatar splats (radius 3-6 px) this
-//     removes most (pixel, splat) evaluations of a 16x16 tile; every dropped pair is one App. A.3 would skip;
-//   * warps retire independently (all 32 pixels saturated, T(1-a) < 1e-4) and the CTA stops staging when all have;
-//   * exp via a single MUFU.EX2 on the pre-scaled conic; outputs leave as 16-byte vector stores.
+// Design (B200).  The kernel is issue- and latency-bound, not HBM-bound (ncu in
+// profiles/), so the structure removes per-pixel work and idle SMs rather than bytes:
+//   * work unit = one 8x8 quarter of a 16x16 tile, one 64-thread CTA (2 warps, each an 8x4 pixel rect).  Tile cost
+//     spans three orders of magnitude; quarter-tile CTAs launched longest-list-first (cx.tile_order) keep all 148 SMs
+//     busy where whole-tile CTAs in index order left them idle > 50 % of the time (profiles/r01_notes.md);
+//   * the tile's depth-sorted id list is streamed in batches of 128; each thread gathers two 48-byte splat records
+//     (three 16-byte cp.async = LDGSTS each, no register staging) into a double-buffered shared-memory stage while
+//     the previous batch is composited;
+//   * for every 32 staged splats a warp runs ONE lane-parallel test "can this splat reach alpha >= 1/255 anywhere in
+//     my 8x4 rect" (region_max_p2), ballots, and walks only the survivors with lanes = pixels.  For ExAvatar's
+//     millimetre-scale avatar splats (radius 3-6 px) this removes most (pixel, splat) evaluations of a 16x16 tile;
+//     every dropped pair is one App. A.3 would skip anyway;
+//   * warps retire independently (all 32 pixels saturated, T(1-a) < 1e-4); the CTA stops staging when both have;
+//   * exp via one MUFU.EX2 on the pre-scaled conic; outputs leave as 16-byte vector stores.
 #include "common.cuh"
 
 namespace b2r {
 
-constexpr int FWD_BATCH = 256;
+constexpr int FWD_THREADS = 64;
+constexpr int FWD_BATCH = 128;
+constexpr int FWD_PER_THREAD = FWD_BATCH / FWD_THREADS;
 
 struct FwdStage {
   float4 a[FWD_BATCH];  // px, py, A2, B2
@@ -37,14 +42,16 @@ __device__ __forceinline__ void store4(float* base, bool vec_ok, int lane, float
   }
 }
 
-__global__ void __launch_bounds__(256) composite_fwd_kernel(const B2RScene sc, const Ctx cx, const B2RForwardOutputs out,
-                                                            const int vec_ok) {
+__global__ void __launch_bounds__(FWD_THREADS) composite_fwd_kernel(const B2RScene sc, const Ctx cx,
+                                                                    const B2RForwardOutputs out, const int vec_ok) {
   __shared__ FwdStage stage[2];
-  const int tile = blockIdx.x;
+  const int tile = (int)cx.tile_order[blockIdx.x >> 2];
+  const int quad = blockIdx.x & 3;
   const int tx = tile % cx.gx, ty = tile / cx.gx;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const int W = sc.width, H = sc.height;
-  const int wx0 = tx * TILE + (warp & 1) * 8, wy0 = ty * TILE + (warp >> 1) * 4;
+  const int wx0 = tx * TILE + (quad & 1) * 8, wy0 = ty * TILE + (quad >> 1) * 8 + warp * 4;
+  if (wx0 >= W || ty * TILE + (quad >> 1) * 8 >= H) return;  // quarter entirely outside the image (CTA-uniform)
   const int px = wx0 + (lane & 7), py = wy0 + (lane >> 3);
   const bool inside = px < W && py < H;
   const float pxf = (float)px, pyf = (float)py;
@@ -61,14 +68,18 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const B2RScene sc, c
   bool done = !inside;
 
   auto issue = [&](int b) {
-    const int idx = b * FWD_BATCH + threadIdx.x;
-    if (idx < n) {
-      const uint32_t id = __ldg(ids + idx);
-      const float4* src = reinterpret_cast<const float4*>(cx.geom + id);
-      FwdStage& s = stage[b & 1];
-      cp_async16(&s.a[threadIdx.x], src);
-      cp_async16(&s.b[threadIdx.x], src + 1);
-      cp_async16(&s.c[threadIdx.x], src + 2);
+    FwdStage& s = stage[b & 1];
+#pragma unroll
+    for (int u = 0; u < FWD_PER_THREAD; u++) {
+      const int slot = threadIdx.x + u * FWD_THREADS;
+      const int idx = b * FWD_BATCH + slot;
+      if (idx < n) {
+        const uint32_t id = __ldg(ids + idx);
+        const float4* src = reinterpret_cast<const float4*>(cx.geom + id);
+        cp_async16(&s.a[slot], src);
+        cp_async16(&s.b[slot], src + 1);
+        cp_async16(&s.c[slot], src + 2);
+      }
     }
     cp_async_commit();
   };
@@ -92,34 +103,55 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const B2RScene sc, c
         hit = !(region_max_p2(a.x, a.y, a.z, a.w, bb.x, rx0, ry0, rx1, ry1) < bb.w);
       }
       unsigned mask = __ballot_sync(0xffffffffu, hit);
+      // Walk the surviving splats two at a time: the two exponent evaluations are independent (ILP 2); only the
+      // transmittance recurrence is serial, and it is applied branch-free (selects), so the only branches in this
+      // loop are warp-uniform.
       while (mask) {
-        const int k = __ffs(mask) - 1;
+        const int k0 = __ffs(mask) - 1;
         mask &= mask - 1;
-        const int j = c0 + k;
-        const float4 a = s.a[j];
-        const float4 bb = s.b[j];
-        const float4 col = s.c[j];
-        if (!done) {
-          const float dx = a.x - pxf, dy = a.y - pyf;
-          const float p2 = a.z * dx * dx + bb.x * dy * dy + a.w * dx * dy;
-          if (p2 <= 0.f) {
-            const float alpha = fminf(K_ALPHA_MAX, bb.y * ex2_approx(p2));
-            if (alpha >= K_ALPHA_MIN) {
-              const float test = T * (1.f - alpha);
-              if (test < K_T_MIN) {
-                done = true;  // this splat is not applied (App. A.3)
-              } else {
-                const float w = alpha * T;
-                Cr = fmaf(col.x, w, Cr);
-                Cg = fmaf(col.y, w, Cg);
-                Cb = fmaf(col.z, w, Cb);
-                Dp = fmaf(bb.z, w, Dp);
-                Aa += w;
-                T = test;
-                last = (uint32_t)(b * FWD_BATCH + j + 1);
-              }
-            }
-          }
+        const bool two = mask != 0;
+        const int k1 = two ? __ffs(mask) - 1 : k0;
+        mask &= mask - 1;  // no-op when mask == 0
+        const int j0 = c0 + k0, j1 = c0 + k1;
+        const float4 a0 = s.a[j0], b0 = s.b[j0], col0 = s.c[j0];
+        const float4 a1 = s.a[j1], b1 = s.b[j1], col1 = s.c[j1];
+        const float dx0 = a0.x - pxf, dy0 = a0.y - pyf;
+        const float dx1 = a1.x - pxf, dy1 = a1.y - pyf;
+        const float p20 = a0.z * dx0 * dx0 + b0.x * dy0 * dy0 + a0.w * dx0 * dy0;
+        const float p21 = a1.z * dx1 * dx1 + b1.x * dy1 * dy1 + a1.w * dx1 * dy1;
+        const float al0 = fminf(K_ALPHA_MAX, b0.y * ex2_approx(p20));
+        const float al1 = fminf(K_ALPHA_MAX, b1.y * ex2_approx(p21));
+        const bool ok0 = (p20 <= 0.f) & (al0 >= K_ALPHA_MIN);
+        const bool ok1 = two & (p21 <= 0.f) & (al1 >= K_ALPHA_MIN);
+        {
+          const bool v = ok0 & !done;
+          const float test = T * (1.f - al0);
+          const bool stop = v & (test < K_T_MIN);  // this splat is not applied (App. A.3)
+          done |= stop;
+          const bool use = v & !stop;
+          const float w = al0 * T;  // predicated accumulates: a skipped splat must not touch the sums at all
+          Cr = use ? fmaf(col0.x, w, Cr) : Cr;
+          Cg = use ? fmaf(col0.y, w, Cg) : Cg;
+          Cb = use ? fmaf(col0.z, w, Cb) : Cb;
+          Dp = use ? fmaf(b0.z, w, Dp) : Dp;
+          Aa = use ? Aa + w : Aa;
+          T = use ? test : T;
+          last = use ? (uint32_t)(b * FWD_BATCH + j0 + 1) : last;
+        }
+        {
+          const bool v = ok1 & !done;
+          const float test = T * (1.f - al1);
+          const bool stop = v & (test < K_T_MIN);
+          done |= stop;
+          const bool use = v & !stop;
+          const float w = al1 * T;  // predicated accumulates: a skipped splat must not touch the sums at all
+          Cr = use ? fmaf(col1.x, w, Cr) : Cr;
+          Cg = use ? fmaf(col1.y, w, Cg) : Cg;
+          Cb = use ? fmaf(col1.z, w, Cb) : Cb;
+          Dp = use ? fmaf(b1.z, w, Dp) : Dp;
+          Aa = use ? Aa + w : Aa;
+          T = use ? test : T;
+          last = use ? (uint32_t)(b * FWD_BATCH + j1 + 1) : last;
         }
       }
       warp_live = __any_sync(0xffffffffu, !done);
@@ -127,13 +159,13 @@ __global__ void __launch_bounds__(256) composite_fwd_kernel(const B2RScene sc, c
   }
   cp_async_wait<0>();
 
+  // consumed_fwd counts list entries per TILE: four quarter-CTAs each add a quarter of what they staged
   if (threadIdx.x == 0 && staged) atomicAdd(reinterpret_cast<unsigned long long*>(&cx.status->consumed_fwd), (unsigned long long)staged);
 
   const size_t N = (size_t)W * H;
   const size_t pix = (size_t)py * W + px;
   const float bg0 = __ldg(sc.bg), bg1 = __ldg(sc.bg + 1), bg2 = __ldg(sc.bg + 2);
   const bool v = vec_ok != 0;
-  // rows of a sub-tile outside the image never store; shuffles stay warp-uniform
   store4(out.color + pix, v, lane, fmaf(T, bg0, Cr), inside);
   store4(out.color + N + pix, v, lane, fmaf(T, bg1, Cg), inside);
   store4(out.color + 2 * N + pix, v, lane, fmaf(T, bg2, Cb), inside);
@@ -147,7 +179,10 @@ int launch_composite_fwd(const B2RScene& sc, const Ctx& cx, const B2RForwardOutp
   auto al16 = [](const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; };
   const int vec_ok = (sc.width % 4 == 0) && al16(out.color) && al16(out.depth) && al16(out.alpha) && al16(cx.final_T) &&
                      al16(cx.n_contrib);
-  composite_fwd_kernel<<<cx.tiles, 256, 0, st>>>(sc, cx, out, vec_ok);
+  {
+    ProfScope p(K_COMPOSITE_FWD, st);
+    composite_fwd_kernel<<<cx.tiles * 4, FWD_THREADS, 0, st>>>(sc, cx, out, vec_ok);
+  }
   return check_launch();
 }
 

@@ -113,24 +113,7 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
           g.g0 = make_float4(px, py, A2, B2);
           g.g1 = make_float4(C2, o, pv.z, thr2);
           g.g2 = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float(bits));
-          // count tiles (with exact culling unless disabled)
-          const bool no_cull = (sc.flags & B2R_FLAG_NO_TILE_CULL) != 0;
-          int kept = 0;
-          for (int ty = y0; ty < y1; ty++)
-            for (int tx = x0; tx < x1; tx++) {
-              bool keep = true;
-              if (!no_cull) {
-                const float rx0 = (float)(tx * TILE), ry0 = (float)(ty * TILE);
-                const float rx1 = fminf(rx0 + (float)(TILE - 1), (float)(cam.W - 1));
-                const float ry1 = fminf(ry0 + (float)(TILE - 1), (float)(cam.H - 1));
-                keep = !(region_max_p2(px, py, A2, B2, C2, rx0, ry0, rx1, ry1) < thr2);
-              }
-              if (keep) {
-                atomicAdd(cx.tile_count + ty * cx.gx + tx, 1u);
-                kept++;
-              }
-            }
-          aux = make_int4(x0 | (y0 << 16), x1 | (y1 << 16), radius, kept);
+          aux = make_int4(x0 | (y0 << 16), x1 | (y1 << 16), radius, (x1 - x0) * (y1 - y0));
         }
       }
     }
@@ -140,6 +123,14 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
     gp[1] = g.g1;
     gp[2] = g.g2;
     cx.aux[i] = aux;
+  }
+  // per-tile histogram of kept (splat, tile) pairs -- warp-cooperative, exact culling unless disabled
+  {
+    const int gx = cx.gx;
+    uint32_t* tile_count = cx.tile_count;
+    warp_for_each_kept_tile(visible, aux.x & 0xffff, aux.x >> 16, aux.y & 0xffff, aux.y >> 16, g.g0.x, g.g0.y, g.g0.z,
+                            g.g0.w, g.g1.x, g.g1.w, 0u, 0u, (sc.flags & B2R_FLAG_NO_TILE_CULL) != 0, sc.width, sc.height,
+                            [&](int tx, int ty, uint32_t, uint32_t) { atomicAdd(tile_count + ty * gx + tx, 1u); });
   }
   const unsigned vis = __ballot_sync(0xffffffffu, visible);
   if ((threadIdx.x & 31) == 0 && vis) atomicAdd(&cx.status->num_visible, (uint32_t)__popc(vis));
@@ -187,6 +178,28 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx) {
     if (threadIdx.x == 1023) carry_s = carry + warp_sums[31];
     __syncthreads();
   }
+  // Longest-list-first processing order for the per-tile kernels (sort, composites): counting sort of the tiles
+  // by floor(log2(n)) descending.  Tile cost is ~linear in n and spans three orders of magnitude, so launching in
+  // index order leaves most SMs idle behind a few heavy tiles that happened to start late.
+  __shared__ uint32_t bin_cursor[34];
+  if (threadIdx.x < 34) bin_cursor[threadIdx.x] = 0;
+  __syncthreads();
+  auto bin_of = [](uint32_t n) { return n == 0 ? 33 : __clz(n); };  // clz = 31 - floor(log2 n): small bin = long list
+  for (int t = threadIdx.x; t < cx.tiles; t += blockDim.x) atomicAdd(&bin_cursor[bin_of(cx.tile_count[t])], 1u);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    uint32_t run = 0;
+    for (int b = 0; b < 34; b++) {
+      const uint32_t c = bin_cursor[b];
+      bin_cursor[b] = run;
+      run += c;
+    }
+  }
+  __syncthreads();
+  for (int t = threadIdx.x; t < cx.tiles; t += blockDim.x) {
+    const uint32_t pos = atomicAdd(&bin_cursor[bin_of(cx.tile_count[t])], 1u);
+    cx.tile_order[pos] = (uint32_t)t;
+  }
   if (threadIdx.x == 0) {
     const uint64_t total = carry_s;
     cx.status->num_dups = total;
@@ -222,15 +235,19 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 
 int launch_project(const B2RScene& sc, const Ctx& cx, int32_t* radii, cudaStream_t st) {
   cudaMemsetAsync(cx.tile_count, 0, (size_t)cx.tiles * 4, st);
-  status_reset_kernel<<<1, 1, 0, st>>>(cx);
-  if (sc.P > 0) project_kernel<<<(sc.P + 255) / 256, 256, 0, st>>>(sc, cx, radii);
-  tile_scan_kernel<<<1, 1024, 0, st>>>(cx);
+  { ProfScope p(K_MISC, st); status_reset_kernel<<<1, 1, 0, st>>>(cx); }
+  if (sc.P > 0) { ProfScope p(K_PROJECT, st); project_kernel<<<(sc.P + 255) / 256, 256, 0, st>>>(sc, cx, radii); }
+  { ProfScope p(K_TILE_SCAN, st); tile_scan_kernel<<<1, 1024, 0, st>>>(cx); }
   return check_launch();
 }
 
-void launch_tile_scan(const Ctx& cx, cudaStream_t st) { tile_scan_kernel<<<1, 1024, 0, st>>>(cx); }
+void launch_tile_scan(const Ctx& cx, cudaStream_t st) {
+  ProfScope p(K_TILE_SCAN, st);
+  tile_scan_kernel<<<1, 1024, 0, st>>>(cx);
+}
 
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t st) {
+  ProfScope p(K_MISC, st, P > 0 ? 1 : 0);
   if (P > 0) mark_visible_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, view, present);
   return check_launch();
 }

@@ -18,6 +18,8 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
   const int M = sc.sh_coeffs;
   const int4 aux = cx.aux[i];
   const bool visible = aux.z > 0;
+  const bool accumulate = (out.flags & B2R_BWD_ACCUMULATE) != 0;
+  if (accumulate && !visible) return;  // nothing to add
 
   float dm[3] = {0.f, 0.f, 0.f}, dm2[2] = {0.f, 0.f}, dcol[3] = {0.f, 0.f, 0.f}, dop = 0.f;
   float dS[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -157,7 +159,9 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
       for (int c = 0; c < 3; c++) {
         const float gc = ((clamp_bits >> c) & 1u) ? 0.f : dcol[c];
         auto SH = [&](int k) { return __ldg(sh + k * 3 + c); };
-        auto DSH = [&](int k, float basis) { dsh[k * 3 + c] = basis * gc; };
+        auto DSH = [&](int k, float basis) {
+          if (accumulate) dsh[k * 3 + c] += basis * gc; else dsh[k * 3 + c] = basis * gc;
+        };
         float drx = 0.f, dry = 0.f, drz = 0.f;
         DSH(0, B2R_SH_C0);
         if (deg > 0) {
@@ -189,7 +193,7 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
             }
           }
         }
-        for (int k = used; k < M; k++) dsh[k * 3 + c] = 0.f;
+        if (!accumulate) for (int k = used; k < M; k++) dsh[k * 3 + c] = 0.f;
         ddir[0] += drx * gc;
         ddir[1] += dry * gc;
         ddir[2] += drz * gc;
@@ -201,38 +205,39 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
     }
   }
 
-  if (out.dL_dmeans3D) {
-    out.dL_dmeans3D[3 * (size_t)i] = dm[0];
-    out.dL_dmeans3D[3 * (size_t)i + 1] = dm[1];
-    out.dL_dmeans3D[3 * (size_t)i + 2] = dm[2];
-  }
-  if (out.dL_dmeans2D) {
-    out.dL_dmeans2D[3 * (size_t)i] = dm2[0];
-    out.dL_dmeans2D[3 * (size_t)i + 1] = dm2[1];
-    out.dL_dmeans2D[3 * (size_t)i + 2] = 0.f;
-  }
-  if (out.dL_dcolors) {
-    out.dL_dcolors[3 * (size_t)i] = dcol[0];
-    out.dL_dcolors[3 * (size_t)i + 1] = dcol[1];
-    out.dL_dcolors[3 * (size_t)i + 2] = dcol[2];
-  }
-  if (out.dL_dopacities) out.dL_dopacities[i] = dop;
-  if (out.dL_dscales) {
-    out.dL_dscales[3 * (size_t)i] = dscale[0];
-    out.dL_dscales[3 * (size_t)i + 1] = dscale[1];
-    out.dL_dscales[3 * (size_t)i + 2] = dscale[2];
+  auto put3 = [&](float* base, const float* v) {
+    if (!base) return;
+    float* d = base + 3 * (size_t)i;
+    if (accumulate) { d[0] += v[0]; d[1] += v[1]; d[2] += v[2]; }
+    else { d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; }
+  };
+  const float dm2z[3] = {dm2[0], dm2[1], 0.f};
+  put3(out.dL_dmeans3D, dm);
+  put3(out.dL_dmeans2D, dm2z);
+  put3(out.dL_dcolors, dcol);
+  put3(out.dL_dscales, dscale);
+  if (out.dL_dopacities) {
+    if (accumulate) out.dL_dopacities[i] += dop; else out.dL_dopacities[i] = dop;
   }
   if (out.dL_drotations) {
 #pragma unroll
-    for (int k = 0; k < 4; k++) out.dL_drotations[4 * (size_t)i + k] = dq[k];
+    for (int k = 0; k < 4; k++) {
+      float* d = out.dL_drotations + 4 * (size_t)i + k;
+      if (accumulate) *d += dq[k]; else *d = dq[k];
+    }
   }
   if (out.dL_dcov3D) {
 #pragma unroll
-    for (int k = 0; k < 6; k++) out.dL_dcov3D[6 * (size_t)i + k] = sc.cov3D_precomp ? dS[k] : 0.f;
+    for (int k = 0; k < 6; k++) {
+      float* d = out.dL_dcov3D + 6 * (size_t)i + k;
+      const float v = sc.cov3D_precomp ? dS[k] : 0.f;
+      if (accumulate) *d += v; else *d = v;
+    }
   }
 }
 
 int launch_project_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, const float* gacc, cudaStream_t st) {
+  ProfScope p(K_PROJECT_BWD, st, sc.P > 0 ? 1 : 0);
   if (sc.P > 0) project_bwd_kernel<<<(sc.P + 255) / 256, 256, 0, st>>>(sc, cx, a, gacc);
   return check_launch();
 }

@@ -1,0 +1,93 @@
+"""`FramePlan`: allocation-free, sync-free, CUDA-graph-capturable use of the C ABI.
+
+The autograd front-end (`rasterizer.py`) must size buffers per call because it cannot know the caller's next scene.
+A training loop that renders the same Gaussian set frame after frame (ExAvatar: avatar/main/train.py:24-57) can do
+better: fix the duplicate capacity once, keep every buffer resident, and enqueue forward + backward with no host
+round-trip at all -- which also makes the whole step capturable in a CUDA graph (`torch.cuda.graph`), so a step of F
+frames costs one graph launch instead of ~9 F kernel launches.  Overflow of the fixed capacity is detected from the
+device status block (`status()`), checked by the caller outside the hot loop.
+
+Gradients are written (or, with `accumulate=True`, summed) into caller-provided tensors, e.g. views of the flat
+bucket that is all-reduced once per step.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib as L
+from .rasterizer import _f32c, _make_scene, _ptr
+
+
+class FramePlan:
+    def __init__(self, P: int, width: int, height: int, dup_capacity: int, device, sh_coeffs: int = 0):
+        self.lib = L.load()
+        self.P, self.W, self.H, self.M = int(P), int(width), int(height), int(sh_coeffs)
+        self.device = torch.device(device)
+        self.capacity = int(dup_capacity)
+        dev = self.device
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        self.color, self.depth, self.alpha = f(3, height, width), f(1, height, width), f(1, height, width)
+        self.radii = torch.empty(P, dtype=torch.int32, device=dev)
+        self.ctx_bytes = self.lib.b2r_ctx_bytes(P, width, height)
+        self.ctx_buf = torch.empty(self.ctx_bytes, dtype=torch.uint8, device=dev)
+        self.ids = torch.empty(max(self.capacity, 1), dtype=torch.int32, device=dev)
+        self.scratch_bytes = self.lib.b2r_scratch_bytes(P, width, height, self.capacity)
+        self.scratch = torch.empty(self.scratch_bytes, dtype=torch.uint8, device=dev)
+        self.bwd_bytes = self.lib.b2r_backward_scratch_bytes(P)
+        self.bwd_scratch = torch.empty(self.bwd_bytes, dtype=torch.uint8, device=dev)
+        self.ws = L.B2RWorkspace(self.ctx_buf.data_ptr(), self.ctx_bytes, self.ids.data_ptr(), self.capacity,
+                                 self.scratch.data_ptr(), self.scratch_bytes, None, 0)
+        self.out = L.B2RForwardOutputs(self.color.data_ptr(), self.depth.data_ptr(), self.alpha.data_ptr(),
+                                       self.radii.data_ptr())
+        self._scenes = {}
+
+    def scene(self, key, settings, assets: Dict[str, torch.Tensor], flags: int = 0):
+        """Builds (and caches under `key`) the B2RScene for one frame; tensors must stay alive and in place."""
+        if key in self._scenes:
+            return self._scenes[key][0]
+        g = lambda k: None if assets.get(k) is None else _f32c(assets[k], k)
+        shs = g("shs") if self.M > 0 else None
+        sc, keep = _make_scene(settings, g("mean_3d"), shs, None if shs is not None else g("rgb"), g("opacity"),
+                               g("scale"), g("rotation"), None, flags)
+        self._scenes[key] = (sc, keep)
+        return sc
+
+    def forward(self, sc) -> None:
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            L.check(self.lib.b2r_forward(C.byref(sc), C.byref(self.ws), C.byref(self.out), st), "b2r_forward")
+
+    def backward(self, sc, g_color: torch.Tensor, grads: Dict[str, Optional[torch.Tensor]], accumulate: bool = False,
+                 g_depth: Optional[torch.Tensor] = None, g_alpha: Optional[torch.Tensor] = None) -> None:
+        """grads keys: means3D, means2D, shs, colors, opacities, scales, rotations, cov3D (missing -> not written)."""
+        a = L.B2RBackwardArgs(_ptr(g_color), _ptr(g_depth), _ptr(g_alpha), _ptr(grads.get("means3D")),
+                              _ptr(grads.get("means2D")), _ptr(grads.get("shs")), _ptr(grads.get("colors")),
+                              _ptr(grads.get("opacities")), _ptr(grads.get("scales")), _ptr(grads.get("rotations")),
+                              _ptr(grads.get("cov3D")), L.B2R_BWD_ACCUMULATE if accumulate else 0, 0)
+        with torch.cuda.device(self.device):
+            st = torch.cuda.current_stream(self.device).cuda_stream
+            L.check(self.lib.b2r_backward(C.byref(sc), C.byref(self.ws), C.byref(a), self.bwd_scratch.data_ptr(),
+                                          self.bwd_bytes, st), "b2r_backward")
+
+    def status(self) -> dict:
+        raw = self.ctx_buf[: C.sizeof(L.B2RStatus)].cpu().numpy().tobytes()
+        s = L.B2RStatus.from_buffer_copy(raw)
+        return {"num_dups": int(s.num_dups), "dup_capacity": int(s.dup_capacity), "overflow": int(s.overflow),
+                "num_visible": int(s.num_visible), "consumed_fwd": int(s.consumed_fwd),
+                "consumed_bwd": int(s.consumed_bwd)}
+
+
+def grad_bucket(P: int, device, sh_coeffs: int = 0):
+    """One flat fp32 buffer holding every per-Gaussian gradient, plus named views into it."""
+    widths = [("means3D", 3), ("means2D", 3), ("opacities", 1), ("scales", 3), ("rotations", 4)]
+    widths.append(("shs", 3 * sh_coeffs) if sh_coeffs > 0 else ("colors", 3))
+    total = sum(w for _, w in widths) * P
+    flat = torch.zeros(total, dtype=torch.float32, device=device)
+    views, o = {}, 0
+    for name, w in widths:
+        views[name] = flat[o:o + w * P].view(P, w) if name != "shs" else flat[o:o + w * P].view(P, sh_coeffs, 3)
+        o += w * P
+    return flat, views

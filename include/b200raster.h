@@ -114,7 +114,11 @@ typedef struct B2RBackwardArgs {
   float* dL_dscales;    /* (P,3) */
   float* dL_drotations; /* (P,4) */
   float* dL_dcov3D;     /* (P,6) */
+  uint32_t flags;       /* B2R_BWD_ACCUMULATE: outputs += gradient instead of outputs = gradient, so the frames a rank
+                           renders in one step sum into a single bucket that is all-reduced once */
+  uint32_t reserved;
 } B2RBackwardArgs;
+#define B2R_BWD_ACCUMULATE 1u
 
 int b2r_abi_version(void);
 const char* b2r_strerror(int code);
@@ -140,6 +144,17 @@ int b2r_backward(const B2RScene* scene, const B2RWorkspace* ws, const B2RBackwar
 
 /* present[i] = 1 iff Gaussian i passes the near-plane test (z_view > 0.2). */
 int b2r_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present, void* stream);
+
+/* Measurement hooks (host side).  Kernel ids: 0 project, 1 tile_scan, 2 scatter, 3 sort_small, 4 sort_large,
+ * 5 composite_fwd, 6 composite_bwd, 7 project_bwd, 8 misc (status reset).  With profiling on, every kernel launch
+ * is bracketed by CUDA events on the caller's stream; b2r_profile_read() waits for them and returns the summed
+ * milliseconds and launch counts per kernel id (arrays of B2R_NUM_KERNELS).  b2r_launch_count() counts kernel
+ * launches made by this library since it was loaded, profiling or not. */
+#define B2R_NUM_KERNELS 9
+void b2r_profile_enable(int on);
+int b2r_profile_read(double* ms_sum, uint64_t* counts, int reset);
+uint64_t b2r_launch_count(void);
+const char* b2r_kernel_name(int id);
 
 /* Stage-level introspection for parity tests (device pointers into ctx; valid until ctx is reused).
  * geom: P x 12 floats {px, py, A2, B2 | C2, opacity, depth, thr2 | r, g, b, bits};  A2,B2,C2 are the conic
