@@ -31,9 +31,15 @@ __device__ __forceinline__ Cam load_cam(const B2RScene& sc) {
   return c;
 }
 
+// View-space point.  Evaluated left to right WITHOUT fma contraction: view depth is the sort key and feeds the
+// near-plane and frustum-clamp decisions, so it is kept bit-identical to the oracle's C expression (and to itself
+// between the forward and backward kernels) -- per-tile list order is then exactly reproducible.
+__device__ __forceinline__ float dot4_rn(float a, float x, float b, float y, float c, float z, float d) {
+  return __fadd_rn(__fadd_rn(__fadd_rn(__fmul_rn(a, x), __fmul_rn(b, y)), __fmul_rn(c, z)), d);
+}
 __device__ __forceinline__ float3 xform4x3(const float3 p, const float* m) {
-  return make_float3(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],
-                     m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14]);
+  return make_float3(dot4_rn(m[0], p.x, m[4], p.y, m[8], p.z, m[12]), dot4_rn(m[1], p.x, m[5], p.y, m[9], p.z, m[13]),
+                     dot4_rn(m[2], p.x, m[6], p.y, m[10], p.z, m[14]));
 }
 __device__ __forceinline__ float4 xform4x4(const float3 p, const float* m) {
   return make_float4(m[0] * p.x + m[4] * p.y + m[8] * p.z + m[12], m[1] * p.x + m[5] * p.y + m[9] * p.z + m[13],

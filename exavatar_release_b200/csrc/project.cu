@@ -229,7 +229,7 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= P) return;
   const float x = means3D[3 * (size_t)i], y = means3D[3 * (size_t)i + 1], z = means3D[3 * (size_t)i + 2];
-  const float vz = view[2] * x + view[6] * y + view[10] * z + view[14];
+  const float vz = dot4_rn(view[2], x, view[6], y, view[10], z, view[14]);
   present[i] = vz > K_NEAR ? 1 : 0;
 }
 

@@ -77,8 +77,8 @@ typedef struct B2RStatus {
   uint64_t consumed_fwd;  /* list entries staged by the forward composite (C_f of the roofline model) */
   uint64_t consumed_bwd;  /* list entries staged by the backward composite (C_b) */
   uint64_t token;         /* B2RWorkspace.status_token of the project phase that filled this block */
-  uint64_t reserved[1];
-} B2RStatus;
+  uint64_t reserved[2];
+} B2RStatus; /* 64 bytes */
 
 /* Caller-owned memory for one forward->backward context. */
 typedef struct B2RWorkspace {

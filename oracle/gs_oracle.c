@@ -700,6 +700,73 @@ void gso_backward(gso_ctx* g, const real* dL_dcolor, const real* dL_ddepth, cons
   free(acc);
 }
 
+/*
+ * Decision-margin analysis for parity tests.  The composite takes discrete decisions per (pixel, splat):
+ * power > 0, alpha < 1/255, T(1-alpha) < 1e-4.  Two fp32 implementations that differ by an ulp in exp() legitimately
+ * take different branches when a pair sits on a threshold, and the pixel then differs by up to ~alpha*T.  This
+ * re-walks the forward and flags every pixel at which some decision had a relative margin below eps (alpha test:
+ * eps_alpha, transmittance test: eps_T, power test: |power| < 1e-6), and every Gaussian listed in such a pixel's
+ * tile (its gradients inherit the flip).  Tests hold flagged elements to a looser bound and assert they are rare.
+ */
+void gso_fragility(const gso_ctx* g, real eps_alpha, real eps_T, uint8_t* pix_mask, uint8_t* gauss_mask) {
+  const int W = g->W, H = g->H, gx = g->gx, Tn = g->gx * g->gy;
+  memset(pix_mask, 0, (size_t)W * H);
+  memset(gauss_mask, 0, (size_t)(g->P > 0 ? g->P : 1));
+#pragma omp parallel for schedule(dynamic, 1)
+  for (int t = 0; t < Tn; t++) {
+    int tx = t % gx, ty = t / gx;
+    int64_t r0 = g->ranges[2 * t], r1 = g->ranges[2 * t + 1];
+    int tile_fragile = 0;
+    for (int ly = 0; ly < TILE; ly++)
+      for (int lx = 0; lx < TILE; lx++) {
+        int px = tx * TILE + lx, py = ty * TILE + ly;
+        if (px >= W || py >= H) continue;
+        real T = 1;
+        int fragile = 0;
+        for (int64_t k = r0; k < r1; k++) {
+          uint32_t id = g->list[k];
+          real dx = g->xy[2 * id] - (real)px, dy = g->xy[2 * id + 1] - (real)py;
+          const real* co = g->conic_o + 4 * (size_t)id;
+          real power = (real)-0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+          if (power > (real)-1e-6 && power < (real)1e-6) fragile = 1;
+          if (power > (real)0) continue;
+          real araw = co[3] * R_EXP(power);
+          real da = araw - K_ALPHA_MIN;
+          if (da < 0) da = -da;
+          /* the exponent is a sum of terms that cancel for thin, rotated splats: its fp32 rounding error scales with
+             the magnitude of the terms, not of the result (a few ulp of `mag`), and alpha inherits it 1:1 */
+          real mag = (real)0.5 * ((co[0] < 0 ? -co[0] : co[0]) * dx * dx + (co[2] < 0 ? -co[2] : co[2]) * dy * dy);
+          real cross = co[1] * dx * dy;
+          mag += cross < 0 ? -cross : cross;
+          if (da <= (eps_alpha + (real)4e-7 * mag) * K_ALPHA_MIN) fragile = 1;
+          real alpha = araw > K_ALPHA_MAX ? K_ALPHA_MAX : araw;
+          if (alpha < K_ALPHA_MIN) continue;
+          real test = T * ((real)1 - alpha);
+          real dt = test - K_T_MIN;
+          if (dt < 0) dt = -dt;
+          if (dt <= eps_T * K_T_MIN) fragile = 1;
+          if (test < K_T_MIN) break;
+          T = test;
+        }
+        if (fragile) {
+          pix_mask[(size_t)py * W + px] = 1;
+          tile_fragile = 1;
+          /* every splat that could contribute here under either outcome of the flipped decision */
+          for (int64_t k = r0; k < r1; k++) {
+            uint32_t id = g->list[k];
+            real dx = g->xy[2 * id] - (real)px, dy = g->xy[2 * id + 1] - (real)py;
+            const real* co = g->conic_o + 4 * (size_t)id;
+            real power = (real)-0.5 * (co[0] * dx * dx + co[2] * dy * dy) - co[1] * dx * dy;
+            if (power > (real)1e-6) continue;
+            if (co[3] * R_EXP(power) < (real)0.5 * K_ALPHA_MIN) continue;
+            gauss_mask[id] = 1; /* benign race: all writers store 1 */
+          }
+        }
+      }
+    (void)tile_fragile;
+  }
+}
+
 /* markVisible [EXT]: z_view > 0.2 (App. A.1 step 1). */
 void gso_mark_visible(int P, const real* means3D, const real* viewmatrix, uint8_t* present) {
   for (int i = 0; i < P; i++) {

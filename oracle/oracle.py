@@ -36,6 +36,8 @@ def _lib(variant: str):
     lib.gso_free.argtypes = [C.c_void_p]
     lib.gso_mark_visible.restype = None
     lib.gso_mark_visible.argtypes = [C.c_int, rp, rp, rp]
+    lib.gso_fragility.restype = None
+    lib.gso_fragility.argtypes = [C.c_void_p, real, real, rp, rp]
     for name in ("gso_num_dups", "gso_consumed_fwd", "gso_consumed_bwd"):
         getattr(lib, name).restype = C.c_int64
         getattr(lib, name).argtypes = [C.c_void_p]
@@ -174,6 +176,20 @@ def backward(ctx: OracleContext, dL_dcolor, dL_ddepth=None, dL_dalpha=None):
                      _ptr(out["shs"]) if M > 0 else None, _ptr(out["colors"]), _ptr(out["opacities"]), _ptr(out["scales"]),
                      _ptr(out["rotations"]), _ptr(out["cov3D"]))
     return out
+
+
+def fragility(ctx: OracleContext, eps_alpha=2e-5, eps_T=2e-3):
+    """(pixel mask (H,W) bool, Gaussian mask (P) bool): where a discrete composite decision sits on its threshold.
+
+    eps_T is wider than eps_alpha on purpose: T is a product of (1 - alpha) factors, and for the near-opaque splats
+    ExAvatar produces (opacity == 1, module.py:565) 1 - alpha cancels catastrophically -- a 1e-6 relative error in
+    alpha ~ 0.99 is a 1e-4 relative error in that factor, in ANY fp32 implementation."""
+    lib = _lib(ctx.variant)
+    real = C.c_float if ctx.variant == "f32" else C.c_double
+    pm = np.zeros((ctx.H, ctx.W), np.uint8)
+    gm = np.zeros((max(ctx.P, 1),), np.uint8)
+    lib.gso_fragility(ctx.handle, real(eps_alpha), real(eps_T), _ptr(pm), _ptr(gm))
+    return pm.astype(bool), gm[: ctx.P].astype(bool)
 
 
 def mark_visible(positions, viewmatrix, variant="f32"):

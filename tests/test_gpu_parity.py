@@ -1,0 +1,398 @@
+"""Parity of the sm_100a CUDA path against the CPU oracle, through the public autograd API and the C ABI (FramePlan).
+
+Tolerance (north_star: "within 1e-4 rel fp32"): for every output tensor, max|x - y| <= 1e-4 * max|y| over all
+elements whose discrete composite decisions (alpha < 1/255, T(1-a) < 1e-4, power > 0) are not on a threshold; the
+oracle marks threshold cases itself (oracle.fragility) -- those must be rare and are held to a loose bound.  For scale:
+the fp32 and fp64 builds of the oracle itself agree to ~1e-5 on this metric (test_oracle_autograd.py).
+Discrete outputs (radii, per-tile sorted id lists) must be identical.
+"""
+import ctypes as C
+
+import numpy as np
+import pytest
+import torch
+
+from util import kat_settings, pack, splat, workload_settings
+from exavatar_release_b200.synthetic import WORKLOADS, make_assets, make_grad_image
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-4
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    return torch.device("cuda:0")
+
+
+def RZ():
+    from exavatar_release_b200 import rasterizer
+    return rasterizer
+
+
+def _check(name, x, y, bad=None, tol=TOL, max_bad_frac=0.02, loose=0.05):
+    x = np.asarray(x, np.float64)
+    y = np.asarray(y, np.float64)
+    assert x.shape == y.shape, name
+    if y.size == 0:
+        return
+    ninf = np.abs(y).max()
+    d = np.abs(x - y)
+    if bad is None:
+        bad = np.zeros(y.shape, bool)
+    viol = d > tol * ninf
+    # (1) every element beyond tolerance is explained by a composite decision sitting on its threshold ...
+    unexplained = viol & ~bad
+    worst = d[~bad].max() if (~bad).any() else 0.0
+    assert not unexplained.any(), f"{name}: max|d|={worst:.3e} vs {tol}*|y|inf={tol * ninf:.3e} ({unexplained.sum()} elements)"
+    # (2) ... such elements are rare (a large splat touches thousands of pixels, so MANY Gaussians are flagged in a
+    # big scene, but a single flipped pixel rarely moves their gradient by 1e-4 of the tensor norm) ...
+    assert viol.mean() <= max_bad_frac * 0.05, f"{name}: {viol.mean():.5f} of elements beyond tolerance"
+    # (3) ... and bounded.
+    if viol.any():
+        assert d[viol].max() <= loose * max(ninf, 1e-30), f"{name}: threshold element off by {d[viol].max():.3e}"
+
+
+def _run_pair(dev, wl_name, yaw=12.0, seed=0, with_da=False, bg=(0.2, 0.6, 0.9), mode=None):
+    rz = RZ()
+    wl = WORKLOADS[wl_name]
+    assets = make_assets(wl_name, seed=seed)
+    st_c = workload_settings(wl_name, yaw=yaw, bg=bg)
+    st_g = workload_settings(wl_name, yaw=yaw, bg=bg, device=dev, settings_cls=rz.GaussianRasterizationSettings)
+    use_sh = wl.sh_degree > 0
+    if use_sh:
+        st_c, st_g = st_c._replace(sh_degree=wl.sh_degree), st_g._replace(sh_degree=wl.sh_degree)
+    kw_o = dict(shs=assets["shs"]) if use_sh else dict(colors_precomp=assets["rgb"])
+    oc, orad, od, oa, octx = O.forward(st_c, assets["mean_3d"], assets["opacity"], scales=assets["scale"],
+                                       rotations=assets["rotation"], **kw_o)
+    g = {k: v.to(dev).requires_grad_() for k, v in assets.items()}
+    m2 = torch.zeros(g["mean_3d"].shape[0], 3, device=dev, requires_grad=True)
+    rast = rz.GaussianRasterizer(st_g)
+    color, radii, depth, alpha = rast(means3D=g["mean_3d"], means2D=m2, opacities=g["opacity"],
+                                      shs=g["shs"] if use_sh else None, colors_precomp=None if use_sh else g["rgb"],
+                                      scales=g["scale"], rotations=g["rotation"])
+    pm, gm = O.fragility(octx)
+    assert np.array_equal(radii.cpu().numpy(), orad), "radii must be identical"
+    _check("color", color.detach().cpu().numpy(), oc, np.broadcast_to(pm, oc.shape))
+    _check("depth", depth.detach().cpu().numpy(), od, pm[None])
+    _check("alpha", alpha.detach().cpu().numpy(), oa, pm[None])
+    gi = make_grad_image(wl_name, seed)
+    loss = (color * gi.to(dev)).sum()
+    gd = ga = None
+    if with_da:
+        gen = torch.Generator().manual_seed(77)
+        gd = torch.randn(1, wl.height, wl.width, generator=gen)
+        ga = torch.randn(1, wl.height, wl.width, generator=gen)
+        loss = loss + (depth * gd.to(dev)).sum() + (alpha * ga.to(dev)).sum()
+    loss.backward()
+    og = O.backward(octx, gi.numpy(), None if gd is None else gd.numpy()[0], None if ga is None else ga.numpy()[0])
+    row = lambda a: np.broadcast_to(gm.reshape((-1,) + (1,) * (a.ndim - 1)), a.shape)
+    pairs = [("means3D", g["mean_3d"].grad), ("means2D", m2.grad), ("opacities", g["opacity"].grad),
+             ("scales", g["scale"].grad), ("rotations", g["rotation"].grad)]
+    pairs.append(("shs", g["shs"].grad) if use_sh else ("colors", g["rgb"].grad))
+    for k, t in pairs:
+        y = og[k]
+        if np.abs(y).max() == 0:  # e.g. rotations of an all-isotropic avatar
+            assert np.abs(t.cpu().numpy()).max() <= 1e-6
+            continue
+        _check("d_" + k, t.cpu().numpy().reshape(y.shape), y, row(y), max_bad_frac=0.2)
+    assert torch.all(m2.grad[:, 2] == 0)
+    return octx, (color, radii, depth, alpha)
+
+
+@pytest.mark.parametrize("wl,yaw,da", [("T0", 12.0, False), ("T1", 12.0, True), ("T1", -30.0, False), ("T2", 12.0, True),
+                                       ("C1", 12.0, False)])
+def test_forward_backward_parity(dev, wl, yaw, da):
+    _run_pair(dev, wl, yaw=yaw, with_da=da)
+
+
+def test_full_size_c2_parity(dev):
+    """BASELINE configs[1]: 512x512, 100k splats; the oracle needs ~1 s for it."""
+    _run_pair(dev, "C2", yaw=5.0)
+
+
+def _stage_buffers(dev, wl_name, no_cull):
+    """Runs the C ABI directly and returns geometry / lists for stage-level comparison."""
+    from exavatar_release_b200 import _lib as L
+    from exavatar_release_b200.plan import FramePlan
+    rz = RZ()
+    wl = WORKLOADS[wl_name]
+    assets = {k: v.to(dev) for k, v in make_assets(wl_name, seed=0).items()}
+    st = workload_settings(wl_name, yaw=12.0, device=dev, settings_cls=rz.GaussianRasterizationSettings)
+    P = assets["mean_3d"].shape[0]
+    plan = FramePlan(P, wl.width, wl.height, 4_000_000, dev)
+    sc = plan.scene(0, st, assets, flags=L.B2R_FLAG_NO_TILE_CULL if no_cull else 0)
+    plan.forward(sc)
+    torch.cuda.synchronize()
+    lib = plan.lib
+    buf = plan.ctx_buf.cpu().numpy()
+    base = plan.ctx_buf.data_ptr()
+    tiles = ((wl.width + 15) // 16) * ((wl.height + 15) // 16)
+    off = lambda fn: fn(C.byref(plan.ws), P, wl.width, wl.height) - base
+    geom = np.frombuffer(buf[off(lib.b2r_ctx_geom):off(lib.b2r_ctx_geom) + P * 48].tobytes(), np.float32).reshape(P, 12)
+    aux = np.frombuffer(buf[off(lib.b2r_ctx_aux):off(lib.b2r_ctx_aux) + P * 16].tobytes(), np.int32).reshape(P, 4)
+    ranges = np.frombuffer(buf[off(lib.b2r_ctx_ranges):off(lib.b2r_ctx_ranges) + tiles * 8].tobytes(), np.uint32).reshape(tiles, 2)
+    ids = plan.ids.cpu().numpy().view(np.uint32)
+    return geom, aux, ranges, ids, plan.status(), plan
+
+
+def test_stage_geometry_matches_oracle(dev):
+    geom, aux, ranges, ids, status, _ = _stage_buffers(dev, "T1", no_cull=True)
+    assets = make_assets("T1", seed=0)
+    st = workload_settings("T1", yaw=12.0)
+    _, orad, _, _, ctx = O.forward(st, assets["mean_3d"], assets["opacity"], colors_precomp=assets["rgb"],
+                                   scales=assets["scale"], rotations=assets["rotation"])
+    vis = orad > 0
+    assert np.array_equal(aux[:, 2], orad)
+    assert status["num_visible"] == int(vis.sum())
+    assert np.allclose(geom[vis, 0:2], ctx.xy()[vis], rtol=0, atol=2e-4)
+    assert np.allclose(geom[vis, 6], ctx.depth()[vis], rtol=1e-6)
+    L2E = 1.4426950408889634
+    co = ctx.conic_opacity()[vis]
+    assert np.allclose(geom[vis, 2] / (-0.5 * L2E), co[:, 0], rtol=2e-5, atol=1e-7)
+    assert np.allclose(geom[vis, 3] / (-L2E), co[:, 1], rtol=2e-5, atol=1e-6)
+    assert np.allclose(geom[vis, 4] / (-0.5 * L2E), co[:, 2], rtol=2e-5, atol=1e-7)
+    rect = ctx.rect()[vis]
+    assert np.array_equal(aux[vis, 0] & 0xffff, rect[:, 0]) and np.array_equal(aux[vis, 0] >> 16, rect[:, 1])
+    assert np.array_equal(aux[vis, 1] & 0xffff, rect[:, 2]) and np.array_equal(aux[vis, 1] >> 16, rect[:, 3])
+
+
+def test_per_tile_sorted_lists_identical_without_culling(dev):
+    geom, aux, ranges, ids, status, _ = _stage_buffers(dev, "T1", no_cull=True)
+    assets = make_assets("T1", seed=0)
+    st = workload_settings("T1", yaw=12.0)
+    *_, ctx = O.forward(st, assets["mean_3d"], assets["opacity"], colors_precomp=assets["rgb"], scales=assets["scale"],
+                        rotations=assets["rotation"])
+    assert status["num_dups"] == ctx.num_dups
+    o_ids, o_ranges = ctx.sorted_ids(), ctx.ranges()
+    for t in range(ranges.shape[0]):
+        mine = ids[ranges[t, 0]:ranges[t, 1]]
+        ref = o_ids[o_ranges[t, 0]:o_ranges[t, 1]]
+        assert np.array_equal(mine, ref), f"tile {t}"
+
+
+def test_culled_lists_are_ordered_subsets(dev):
+    geom, aux, ranges, ids, status, _ = _stage_buffers(dev, "T1", no_cull=False)
+    assets = make_assets("T1", seed=0)
+    st = workload_settings("T1", yaw=12.0)
+    *_, ctx = O.forward(st, assets["mean_3d"], assets["opacity"], colors_precomp=assets["rgb"], scales=assets["scale"],
+                        rotations=assets["rotation"])
+    assert status["num_dups"] < ctx.num_dups  # the exact tile test removes pairs ...
+    o_ids, o_ranges = ctx.sorted_ids(), ctx.ranges()
+    for t in range(ranges.shape[0]):
+        mine = ids[ranges[t, 0]:ranges[t, 1]].tolist()
+        ref = o_ids[o_ranges[t, 0]:o_ranges[t, 1]].tolist()
+        it = iter(ref)
+        assert all(m in it for m in mine), f"tile {t}: culled list is not an ordered subsequence"  # ... and only removes
+
+
+def test_kats_on_gpu(dev):
+    rz = RZ()
+    st = kat_settings(device=dev, settings_cls=rz.GaussianRasterizationSettings, bg=(0.25, 0.5, 0.75))
+    run = lambda sp: rz.GaussianRasterizer(st)(means2D=torch.zeros(len(sp), 3, device=dev),
+                                               **{k: v for k, v in pack(sp, device=dev).items()})
+    c, r, d, a = run([splat((0, 0, 2.0))])  # KAT 1/2
+    assert r.tolist() == [6]
+    assert float(a[0, 15, 15]) == pytest.approx(0.458149, rel=1e-5)
+    assert float(d[0, 15, 15]) == pytest.approx(0.916299, rel=1e-5)
+    assert float(c[0, 15, 15]) == pytest.approx(0.458149 + (1 - 0.458149) * 0.25, rel=1e-5)
+    # KAT 4: three coincident opacity-1 splats centred on pixel (16,16): stop after the first, second not applied
+    sp = [splat((0.03125, 0.03125, 2.0 + 0.1 * i), o=1.0, rgb=col) for i, col in enumerate([(1, 0, 0), (0, 1, 0), (0, 0, 1)])]
+    c, r, d, a = run(sp)
+    assert float(a[0, 16, 16]) == pytest.approx(0.99, rel=1e-6)
+    assert float(c[1, 16, 16]) == pytest.approx(0.01 * 0.5, rel=1e-4)
+    # KAT 6: near plane
+    c, r, d, a = run([splat((0, 0, 0.2)), splat((0, 0, 0.2001))])
+    assert r[0] == 0 and r[1] > 0
+    rast = rz.GaussianRasterizer(st)
+    assert rast.markVisible(torch.tensor([[0, 0, 0.2], [0, 0, 0.2001]], device=dev)).tolist() == [False, True]
+    # KAT 5: equal depth -> lower index in front
+    c, *_ = run([splat((0, 0, 2.0), o=0.9, rgb=(1, 0, 0)), splat((0, 0, 2.0), o=0.9, rgb=(0, 0, 1))])
+    assert float(c[0, 15, 15]) > float(c[2, 15, 15])
+
+
+def test_cov3d_precomp_path(dev):
+    rz = RZ()
+    assets = make_assets("T0", seed=2)
+    P = assets["mean_3d"].shape[0]
+    g = torch.Generator().manual_seed(5)
+    A = torch.randn(P, 3, 3, generator=g) * 0.05
+    S = A @ A.transpose(1, 2) + 1e-4 * torch.eye(3)
+    cov = torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], 1)
+    st_c = workload_settings("T0", yaw=7.0)
+    st_g = workload_settings("T0", yaw=7.0, device=dev, settings_cls=rz.GaussianRasterizationSettings)
+    oc, orad, od, oa, octx = O.forward(st_c, assets["mean_3d"], assets["opacity"], colors_precomp=assets["rgb"], cov3D_precomp=cov)
+    cg = cov.to(dev).requires_grad_()
+    m3 = assets["mean_3d"].to(dev).requires_grad_()
+    color, radii, depth, alpha = rz.GaussianRasterizer(st_g)(
+        means3D=m3, means2D=torch.zeros(P, 3, device=dev), opacities=assets["opacity"].to(dev),
+        colors_precomp=assets["rgb"].to(dev), cov3D_precomp=cg)
+    assert np.array_equal(radii.cpu().numpy(), orad)
+    gi = make_grad_image("T0", 2)
+    (color * gi.to(dev)).sum().backward()
+    og = O.backward(octx, gi.numpy())
+    pm, gm = O.fragility(octx)
+    _check("color", color.detach().cpu().numpy(), oc, np.broadcast_to(pm, oc.shape))
+    _check("d_cov3D", cg.grad.cpu().numpy(), og["cov3D"], np.broadcast_to(gm[:, None], og["cov3D"].shape), max_bad_frac=0.2)
+    _check("d_means3D", m3.grad.cpu().numpy(), og["means3D"], np.broadcast_to(gm[:, None], og["means3D"].shape), max_bad_frac=0.2)
+
+
+def test_five_live_contexts_then_one_backward(dev):
+    """ExAvatar renders five asset sets before the single loss.backward() (model.py:130-162, train.py:46)."""
+    rz = RZ()
+    st = workload_settings("T1", yaw=3.0, device=dev, settings_cls=rz.GaussianRasterizationSettings)
+    losses, leaves = [], []
+    for s in range(5):
+        a = {k: v.to(dev).requires_grad_() for k, v in make_assets("T1", seed=20 + s).items()}
+        m2 = torch.zeros(a["mean_3d"].shape[0], 3, device=dev, requires_grad=True)
+        img = rz.GaussianRasterizer(st)(means3D=a["mean_3d"], means2D=m2, opacities=a["opacity"], colors_precomp=a["rgb"],
+                                        scales=a["scale"], rotations=a["rotation"])[0]
+        losses.append((img * make_grad_image("T1", s).to(dev)).sum())
+        leaves.append((a, m2))
+    sum(losses).backward()
+    for s, (a, m2) in enumerate(leaves):
+        b = {k: v.detach().clone().requires_grad_() for k, v in a.items()}
+        m2b = torch.zeros_like(m2, requires_grad=True)
+        img = rz.GaussianRasterizer(st)(means3D=b["mean_3d"], means2D=m2b, opacities=b["opacity"], colors_precomp=b["rgb"],
+                                        scales=b["scale"], rotations=b["rotation"])[0]
+        (img * make_grad_image("T1", s).to(dev)).sum().backward()
+        for k in a:
+            assert torch.allclose(a[k].grad, b[k].grad, rtol=1e-4, atol=1e-4 * float(b[k].grad.abs().max())), (s, k)
+        assert torch.allclose(m2.grad, m2b.grad, rtol=1e-4, atol=1e-4 * float(m2b.grad.abs().max()))
+
+
+def test_forward_is_deterministic_and_capacity_modes_agree(dev, monkeypatch):
+    rz = RZ()
+    st = workload_settings("T1", yaw=12.0, device=dev, settings_cls=rz.GaussianRasterizationSettings)
+    a = {k: v.to(dev) for k, v in make_assets("T1", seed=0).items()}
+    P = a["mean_3d"].shape[0]
+
+    def render():
+        return rz.GaussianRasterizer(st)(means3D=a["mean_3d"], means2D=torch.zeros(P, 3, device=dev), opacities=a["opacity"],
+                                         colors_precomp=a["rgb"], scales=a["scale"], rotations=a["rotation"])
+
+    monkeypatch.setattr(rz, "CAPACITY_MODE", "exact")
+    ref = render()
+    again = render()
+    for x, y in zip(ref, again):
+        assert torch.equal(x, y)  # sort key (depth, id) makes the pipeline independent of atomic arrival order
+    monkeypatch.setattr(rz, "CAPACITY_MODE", "speculative")
+    spec = render()
+    for x, y in zip(ref, spec):
+        assert torch.equal(x, y)
+    # a misprediction (capacity far too small) must be repaired transparently
+    rz._state(dev).predicted[(P, st.image_width, st.image_height)] = 10
+    monkeypatch.setattr(rz, "CAPACITY_HEADROOM", 1.0)
+    small = render()
+    for x, y in zip(ref, small):
+        assert torch.equal(x, y)
+
+
+def test_properties_at_full_size(dev):
+    """Size-independent properties on BASELINE configs[1] (C2)."""
+    rz = RZ()
+    wl = WORKLOADS["C2"]
+    a = {k: v.to(dev) for k, v in make_assets("C2", seed=1).items()}
+    P = a["mean_3d"].shape[0]
+    bg1, bg2 = (0.0, 0.0, 0.0), (1.0, 0.5, 0.25)
+
+    def render(assets, bg, perm=None):
+        st = workload_settings("C2", yaw=-9.0, bg=bg, device=dev, settings_cls=rz.GaussianRasterizationSettings)
+        if perm is not None:
+            assets = {k: v[perm] for k, v in assets.items()}
+        return rz.GaussianRasterizer(st)(means3D=assets["mean_3d"], means2D=torch.zeros(P, 3, device=dev),
+                                         opacities=assets["opacity"], colors_precomp=assets["rgb"], scales=assets["scale"],
+                                         rotations=assets["rotation"])
+
+    c1, r1, d1, a1 = render(a, bg1)
+    c2, r2, d2, a2 = render(a, bg2)
+    # background enters linearly through the final transmittance only: c2 - c1 = T * (bg2 - bg1), depth/alpha untouched
+    T = (c2[0] - c1[0])
+    assert torch.equal(d1, d2) and torch.equal(a1, a2) and torch.equal(r1, r2)
+    assert torch.allclose(c2[1] - c1[1], 0.5 * T, atol=2e-6) and torch.allclose(c2[2] - c1[2], 0.25 * T, atol=2e-6)
+    assert torch.allclose(T, 1 - a1[0], atol=2e-5)  # alpha = sum alpha_i T_i = 1 - T_final
+    assert float(T.min()) >= 0 and float(a1.max()) <= 1 + 1e-5
+    # permutation of the input order: radii permute; the image can only change where two splats share a view depth
+    # bit for bit (index tie-break, App. A.2) -- a handful of pairs among 1e5 fp32 depths
+    perm = torch.randperm(P, generator=torch.Generator().manual_seed(3)).to(dev)
+    cp, rp, dp, ap = render(a, bg1, perm)
+    assert torch.equal(rp, r1[perm])
+    assert float((cp != c1).float().mean()) < 1e-3 and torch.allclose(cp, c1, atol=2e-2)
+    assert torch.allclose(dp, d1, atol=0.2)
+    # zero-opacity Gaussians are a no-op
+    extra = {k: torch.cat([v, v[:1000]]) for k, v in a.items()}
+    extra["opacity"][-1000:] = 0.0
+    st = workload_settings("C2", yaw=-9.0, bg=bg1, device=dev, settings_cls=rz.GaussianRasterizationSettings)
+    ce = rz.GaussianRasterizer(st)(means3D=extra["mean_3d"], means2D=torch.zeros(P + 1000, 3, device=dev),
+                                   opacities=extra["opacity"], colors_precomp=extra["rgb"], scales=extra["scale"],
+                                   rotations=extra["rotation"])[0]
+    assert torch.equal(ce, c1)
+
+
+def test_accumulate_mode_sums_frames(dev):
+    """B2R_BWD_ACCUMULATE: two frames summed in place == sum of two separate backward passes."""
+    from exavatar_release_b200.plan import FramePlan, grad_bucket
+    rz = RZ()
+    wl = WORKLOADS["T1"]
+    a = {k: v.to(dev) for k, v in make_assets("T1", seed=0).items()}
+    P = a["mean_3d"].shape[0]
+    plan = FramePlan(P, wl.width, wl.height, 1_000_000, dev)
+    sts = [workload_settings("T1", yaw=y, device=dev, settings_cls=rz.GaussianRasterizationSettings) for y in (-10.0, 10.0)]
+    gis = [make_grad_image("T1", s).to(dev) for s in (0, 1)]
+    scenes = [plan.scene(i, sts[i], a) for i in range(2)]
+    flat_acc, v_acc = grad_bucket(P, dev)
+    sep = []
+    for i in range(2):
+        plan.forward(scenes[i])
+        plan.backward(scenes[i], gis[i], v_acc, accumulate=(i > 0))
+        flat_i, v_i = grad_bucket(P, dev)
+        plan.backward(scenes[i], gis[i], v_i, accumulate=False)
+        sep.append(flat_i)
+    torch.cuda.synchronize()
+    ref = sep[0] + sep[1]
+    assert torch.allclose(flat_acc, ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()))
+    assert plan.status()["overflow"] == 0
+
+
+def test_cuda_graph_replay_matches_eager(dev):
+    from exavatar_release_b200.plan import FramePlan, grad_bucket
+    rz = RZ()
+    wl = WORKLOADS["T1"]
+    a = {k: v.to(dev) for k, v in make_assets("T1", seed=0).items()}
+    P = a["mean_3d"].shape[0]
+    plan = FramePlan(P, wl.width, wl.height, 1_000_000, dev)
+    st = workload_settings("T1", yaw=4.0, device=dev, settings_cls=rz.GaussianRasterizationSettings)
+    gi = make_grad_image("T1", 0).to(dev)
+    sc = plan.scene(0, st, a)
+    flat, views = grad_bucket(P, dev)
+
+    def body():
+        plan.forward(sc)
+        plan.backward(sc, gi, views)
+
+    body()
+    torch.cuda.synchronize()
+    eager_img, eager_grad = plan.color.clone(), flat.clone()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        body()
+    plan.color.zero_()
+    flat.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(plan.color, eager_img)
+    assert torch.allclose(flat, eager_grad, rtol=1e-4, atol=1e-5 * float(eager_grad.abs().max()))
+
+
+def test_renderer_end_to_end_on_gpu(dev):
+    from exavatar_release_b200 import GaussianRenderer
+    from exavatar_release_b200.camera import look_at_cam_param
+    a = {k: v.to(dev).requires_grad_() for k, v in make_assets("T1", seed=0).items() }
+    out = GaussianRenderer()(a, (96, 128), look_at_cam_param(0.0, (96, 128), device=dev), torch.ones(3, device=dev))
+    P = a["mean_3d"].shape[0]
+    assert out["img"].shape == (3, 96, 128) and out["radius"].shape == (P,) and out["is_vis"].dtype == torch.bool
+    out["img"].mean().backward()
+    assert out["mean_2d"].grad.shape == (P, 3) and float(out["mean_2d"].grad.abs().sum()) > 0
