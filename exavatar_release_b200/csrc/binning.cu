@@ -66,12 +66,150 @@ __device__ __forceinline__ void bitonic_sort(KeyPtr key, const int n, const int 
   }
 }
 
-// Sorts every tile whose list length n satisfies lo < n <= hi; CTAs stride over the tiles (the small class is launched
-// with one CTA per tile, the large class with one CTA per SM so that a frame without long lists costs ~2 us).  Lists
-// longer than SMEM_CAP are sorted in place in global memory by the same network (rare: > 16k splats on one tile).
-template <int SMEM_CAP>
-__global__ void __launch_bounds__(256) sort_tiles_kernel(const Ctx cx, const int lo, const int hi) {
-  extern __shared__ __align__(16) unsigned long long skeys[];
+// ---------------------------------------------------------------------------------------------------------------
+// K3: per-tile sort.  Order contract (App. A.2): ascending view depth, ties by ascending Gaussian index.
+//
+// One CTA per tile (CTAs stride over cx.tile_order, longest list first).  Lists of <= 128 entries use the bitonic
+// network on 64-bit (depth, id) keys.  Longer lists use an LSD radix sort in shared memory on the 32-bit depth bits
+// (positive floats order like unsigned integers) carrying a 16-bit local index:
+//   * 8-bit digits; a digit position on which every key of the tile agrees is skipped (the exponent byte almost
+//     always is), so most tiles need 3 passes;
+//   * each warp owns a contiguous chunk; MATCH.ANY groups equal digits inside a 32-key row, so a pass is a
+//     warp-private histogram (no atomics), one 256-digit scan, and a stable scatter;
+//   * ids are fetched once at the end; runs of bit-identical depths (rare: cloned Gaussians) are put in id order by
+//     an odd-even fix-up, which makes the result independent of the scatter's atomic arrival order.
+// Lists longer than CAP (16384) fall back to the in-place bitonic network in global memory.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int SORT_BITONIC_MAX = 128;
+
+template <int CAP, int THREADS>
+struct RadixSmem {
+  static constexpr int W = THREADS / 32;
+  static constexpr size_t bytes = (size_t)CAP * 12 + (size_t)W * 256 * 2 + 64;
+};
+
+template <int CAP, int THREADS>
+__device__ __forceinline__ void radix_sort_tile(const uint2* __restrict__ src, uint32_t* __restrict__ dst, const int n,
+                                                unsigned char* smem_raw) {
+  constexpr int W = THREADS / 32;
+  uint32_t* keyA = reinterpret_cast<uint32_t*>(smem_raw);
+  uint32_t* keyB = keyA + CAP;
+  uint16_t* idxA = reinterpret_cast<uint16_t*>(keyB + CAP);
+  uint16_t* idxB = idxA + CAP;
+  uint16_t* hist = idxB + CAP;  // [W][256]
+  uint32_t* misc = reinterpret_cast<uint32_t*>(hist + W * 256);  // [0] OR, [1] AND, [2..9] warp totals of the digit scan
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+
+  if (tid == 0) { misc[0] = 0u; misc[1] = 0xffffffffu; }
+  __syncthreads();
+  uint32_t vor = 0u, vand = 0xffffffffu;
+  for (int i = tid; i < n; i += THREADS) {
+    const uint32_t k = src[i].x;
+    keyA[i] = k;
+    idxA[i] = (uint16_t)i;
+    vor |= k;
+    vand &= k;
+  }
+  vor = __reduce_or_sync(0xffffffffu, vor);
+  vand = __reduce_and_sync(0xffffffffu, vand);
+  if (lane == 0) { atomicOr(&misc[0], vor); atomicAnd(&misc[1], vand); }
+  __syncthreads();
+  const uint32_t differ = misc[0] ^ misc[1];
+
+  const int chunk = (((n + W - 1) / W) + 31) & ~31;  // keys per warp, a multiple of 32
+  const int c_begin = min(warp * chunk, n), c_end = min(c_begin + chunk, n);
+  uint32_t* kin = keyA; uint32_t* kout = keyB;
+  uint16_t* iin = idxA; uint16_t* iout = idxB;
+  for (int pass = 0; pass < 4; pass++) {
+    const int shift = 8 * pass;
+    if (((differ >> shift) & 0xffu) == 0u) continue;  // CTA-uniform
+    for (int i = tid; i < W * 256; i += THREADS) hist[i] = 0;
+    __syncthreads();
+    uint16_t* myhist = hist + warp * 256;
+    // pass 1: warp-private digit histogram
+    for (int base = c_begin; base < c_end; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < c_end;
+      const uint32_t d = valid ? ((kin[i] >> shift) & 0xffu) : (256u + lane);
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      if (valid && (peers & ((1u << lane) - 1u)) == 0u) myhist[d] = (uint16_t)(myhist[d] + __popc(peers));
+      __syncwarp();
+    }
+    __syncthreads();
+    // scan: hist[w][d] <- first output slot of (digit d, warp w)
+    uint32_t total = 0;
+    if (tid < 256) {
+      for (int w = 0; w < W; w++) {
+        const uint32_t t = hist[w * 256 + tid];
+        hist[w * 256 + tid] = (uint16_t)total;
+        total += t;
+      }
+    }
+    uint32_t incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    if (tid < 256 && lane == 31) misc[2 + warp] = incl;
+    __syncthreads();
+    if (tid < 256) {
+      uint32_t base = incl - total;
+      for (int w = 0; w < warp; w++) base += misc[2 + w];
+      for (int w = 0; w < W; w++) hist[w * 256 + tid] = (uint16_t)(hist[w * 256 + tid] + base);
+    }
+    __syncthreads();
+    // pass 2: stable scatter
+    for (int base = c_begin; base < c_end; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < c_end;
+      const uint32_t k = valid ? kin[i] : 0u;
+      const uint32_t d = valid ? ((k >> shift) & 0xffu) : (256u + lane);
+      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const unsigned below = peers & ((1u << lane) - 1u);
+      uint32_t start = 0;
+      if (valid && below == 0u) {
+        start = myhist[d];
+        myhist[d] = (uint16_t)(start + __popc(peers));
+      }
+      start = __shfl_sync(0xffffffffu, start, __ffs(peers) - 1);
+      if (valid) {
+        const uint32_t o = start + __popc(below);
+        kout[o] = k;
+        iout[o] = iin[i];
+      }
+      __syncwarp();
+    }
+    __syncthreads();
+    { uint32_t* t = kin; kin = kout; kout = t; }
+    { uint16_t* t = iin; iin = iout; iout = t; }
+  }
+  // ids of the sorted entries (kout is free now)
+  uint32_t* ids = kout;
+  for (int i = tid; i < n; i += THREADS) ids[i] = src[iin[i]].y;
+  __syncthreads();
+  // equal depths: ascending id (odd-even transposition restricted to runs of identical keys)
+  for (;;) {
+    int changed = 0;
+#pragma unroll
+    for (int phase = 0; phase < 2; phase++) {
+      for (int i = 2 * tid + phase; i + 1 < n; i += 2 * THREADS) {
+        if (kin[i] == kin[i + 1]) {
+          const uint32_t a = ids[i], b = ids[i + 1];
+          if (a > b) { ids[i] = b; ids[i + 1] = a; changed = 1; }
+        }
+      }
+      __syncthreads();
+    }
+    if (!__syncthreads_or(changed)) break;
+  }
+  for (int i = tid; i < n; i += THREADS) dst[i] = ids[i];
+  __syncthreads();  // shared memory is reused by the next tile of this CTA
+}
+
+template <int CAP, int THREADS>
+__global__ void __launch_bounds__(THREADS) sort_tiles_kernel(const Ctx cx, const int lo, const int hi) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
   for (int t = blockIdx.x; t < cx.tiles; t += gridDim.x) {
     const uint2 r = cx.ranges[cx.tile_order[t]];  // longest lists first
     const int n = (int)(r.y - r.x);
@@ -82,9 +220,10 @@ __global__ void __launch_bounds__(256) sort_tiles_kernel(const Ctx cx, const int
       if (threadIdx.x == 0) dst[0] = src[0].y;
       continue;
     }
-    int npow2 = 2;
-    while (npow2 < n) npow2 <<= 1;
-    if (n <= SMEM_CAP) {
+    if (n <= SORT_BITONIC_MAX) {
+      unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smem_raw);
+      int npow2 = 2;
+      while (npow2 < n) npow2 <<= 1;
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint2 kv = src[i];
         skeys[i] = ((unsigned long long)kv.x << 32) | kv.y;
@@ -92,10 +231,14 @@ __global__ void __launch_bounds__(256) sort_tiles_kernel(const Ctx cx, const int
       __syncthreads();
       bitonic_sort(skeys, n, npow2);
       for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (uint32_t)skeys[i];
-      __syncthreads();  // skeys is reused by the next tile of this CTA
+      __syncthreads();
+    } else if (n <= CAP) {
+      radix_sort_tile<CAP, THREADS>(src, dst, n, smem_raw);
     } else {
       // global fallback: keys are stored (depth_bits, id) = little-endian (lo, hi) words, so re-pack to depth-major first
       unsigned long long* gk = reinterpret_cast<unsigned long long*>(cx.keys + r.x);
+      int npow2 = 2;
+      while (npow2 < n) npow2 <<= 1;
       for (int i = threadIdx.x; i < n; i += blockDim.x) {
         const uint2 kv = src[i];
         gk[i] = ((unsigned long long)kv.x << 32) | kv.y;
@@ -103,12 +246,13 @@ __global__ void __launch_bounds__(256) sort_tiles_kernel(const Ctx cx, const int
       __syncthreads();
       bitonic_sort(gk, n, npow2);
       for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (uint32_t)gk[i];
+      __syncthreads();
     }
   }
 }
 
-constexpr int SORT_SMALL = 2048;   // 16 KB of keys: several CTAs per SM
-constexpr int SORT_LARGE = 16384;  // 128 KB of keys: one CTA per SM
+constexpr int SORT_SMALL = 2048;   // 256 threads, 28 KB of shared memory: several CTAs per SM
+constexpr int SORT_LARGE = 16384;  // 512 threads, 201 KB of shared memory: one CTA per SM
 
 int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t st) {
   // the two-phase entry re-derives ranges and cursors for the capacity the caller finally chose
@@ -121,11 +265,15 @@ int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  cudaFuncSetAttribute(sort_tiles_kernel<SORT_LARGE>, cudaFuncAttributeMaxDynamicSharedMemorySize, SORT_LARGE * 8);
-  { ProfScope p(K_SORT_SMALL, st); sort_tiles_kernel<SORT_SMALL><<<cx.tiles, 256, SORT_SMALL * 8, st>>>(cx, 0, SORT_SMALL); }
+  constexpr size_t small_bytes = RadixSmem<SORT_SMALL, 256>::bytes, large_bytes = RadixSmem<SORT_LARGE, 512>::bytes;
+  cudaFuncSetAttribute(sort_tiles_kernel<SORT_LARGE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)large_bytes);
+  {
+    ProfScope p(K_SORT_SMALL, st);
+    sort_tiles_kernel<SORT_SMALL, 256><<<cx.tiles, 256, small_bytes, st>>>(cx, 0, SORT_SMALL);
+  }
   {
     ProfScope p(K_SORT_LARGE, st);
-    sort_tiles_kernel<SORT_LARGE><<<cx.tiles < sms ? cx.tiles : sms, 256, SORT_LARGE * 8, st>>>(cx, SORT_SMALL, 0x7fffffff);
+    sort_tiles_kernel<SORT_LARGE, 512><<<cx.tiles < sms ? cx.tiles : sms, 512, large_bytes, st>>>(cx, SORT_SMALL, 0x7fffffff);
   }
   return check_launch();
 }

@@ -68,6 +68,11 @@ _STATES_LOCK = threading.Lock()
 CAPACITY_MODE = os.environ.get("B2R_CAPACITY_MODE", "speculative")  # or "exact"
 CAPACITY_HEADROOM = 1.25
 TILE_CULL = os.environ.get("B2R_TILE_CULL", "1") != "0"
+# Fixed-capacity mode: every render uses this many list entries, nothing is polled or synchronised, so the call is
+# capturable in a CUDA graph (torch.cuda.graph) together with the caller's loss, backward and copies.  Overflow is
+# not repaired on the fly in this mode: check `overflowed()` after the step (outputs are truncated, never corrupt).
+FIXED_CAPACITY = None
+RECENT_CONTEXTS = []  # contexts created in fixed-capacity mode (bounded), for the deferred overflow check
 LAST_STATS = {}  # filled when a caller asks for stats (bench / tests)
 
 
@@ -162,7 +167,7 @@ def _forward_impl(settings, means3D, shs, colors, opac, scales, rots, cov, want_
         stream = torch.cuda.current_stream(dev)
         sptr = stream.cuda_stream
         sc, keep = _make_scene(settings, means3D, shs, colors, opac, scales, rots, cov, flags)
-        st = _state(dev)
+        st = None if FIXED_CAPACITY is not None else _state(dev)  # no pinned allocation inside a graph capture
         ctx_bytes = lib.b2r_ctx_bytes(P, W, H)
         ctx_buf = torch.empty(ctx_bytes, dtype=torch.uint8, device=dev)
         out = L.B2RForwardOutputs(color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), radii.data_ptr())
@@ -176,24 +181,33 @@ def _forward_impl(settings, means3D, shs, colors, opac, scales, rots, cov, want_
             return ws, ids, scratch
 
         key = (P, W, H)
-        with st.lock:
-            token = st.next_token()
-            predicted = st.predicted.get(key) if CAPACITY_MODE == "speculative" else None
-            if predicted is not None:
-                cap = int(predicted * CAPACITY_HEADROOM) + 4096
-                ws, ids, scratch = workspace(cap, token)
-                L.check(lib.b2r_forward(C.byref(sc), C.byref(ws), C.byref(out), sptr), "b2r_forward")
-                num = _wait_mirror(st, token, stream)
-                if num > cap:  # misprediction: redo binning + composite with the exact size
-                    ws, ids, scratch = workspace(num, token)
-                    L.check(lib.b2r_forward_render(C.byref(sc), C.byref(ws), C.byref(out), sptr), "b2r_forward_render")
-            else:
-                ws0 = L.B2RWorkspace(ctx_buf.data_ptr(), ctx_bytes, None, 0, None, 0, st.mirror.data_ptr(), token)
-                L.check(lib.b2r_forward_project(C.byref(sc), C.byref(ws0), radii.data_ptr(), sptr), "b2r_forward_project")
-                num = _wait_mirror(st, token, stream)
-                ws, ids, scratch = workspace(num, token)
-                L.check(lib.b2r_forward_render(C.byref(sc), C.byref(ws), C.byref(out), sptr), "b2r_forward_render")
-            st.predicted[key] = num
+        if FIXED_CAPACITY is not None:
+            cap = int(FIXED_CAPACITY)
+            ids = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
+            sbytes = lib.b2r_scratch_bytes(P, W, H, cap)
+            scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+            ws = L.B2RWorkspace(ctx_buf.data_ptr(), ctx_bytes, ids.data_ptr(), cap, scratch.data_ptr(), sbytes, None, 0)
+            L.check(lib.b2r_forward(C.byref(sc), C.byref(ws), C.byref(out), sptr), "b2r_forward")
+            num = -1
+        else:
+          with st.lock:
+              token = st.next_token()
+              predicted = st.predicted.get(key) if CAPACITY_MODE == "speculative" else None
+              if predicted is not None:
+                  cap = int(predicted * CAPACITY_HEADROOM) + 4096
+                  ws, ids, scratch = workspace(cap, token)
+                  L.check(lib.b2r_forward(C.byref(sc), C.byref(ws), C.byref(out), sptr), "b2r_forward")
+                  num = _wait_mirror(st, token, stream)
+                  if num > cap:  # misprediction: redo binning + composite with the exact size
+                      ws, ids, scratch = workspace(num, token)
+                      L.check(lib.b2r_forward_render(C.byref(sc), C.byref(ws), C.byref(out), sptr), "b2r_forward_render")
+              else:
+                  ws0 = L.B2RWorkspace(ctx_buf.data_ptr(), ctx_bytes, None, 0, None, 0, st.mirror.data_ptr(), token)
+                  L.check(lib.b2r_forward_project(C.byref(sc), C.byref(ws0), radii.data_ptr(), sptr), "b2r_forward_project")
+                  num = _wait_mirror(st, token, stream)
+                  ws, ids, scratch = workspace(num, token)
+                  L.check(lib.b2r_forward_render(C.byref(sc), C.byref(ws), C.byref(out), sptr), "b2r_forward_render")
+              st.predicted[key] = num
         # `scratch` may be recycled by the caching allocator as soon as we drop it: same-stream ordering makes that safe
         if settings.debug:
             stream.synchronize()
@@ -203,10 +217,25 @@ def _forward_impl(settings, means3D, shs, colors, opac, scales, rots, cov, want_
         cx.P, cx.W, cx.H, cx.M, cx.flags = P, W, H, sc.sh_coeffs, flags
         # the saved workspace must not point at the recycled scratch
         cx.ws = L.B2RWorkspace(ctx_buf.data_ptr(), ctx_bytes, ids.data_ptr(), ws.dup_capacity, None, 0, None, 0)
+        if FIXED_CAPACITY is not None:
+            RECENT_CONTEXTS.append(cx)
+            del RECENT_CONTEXTS[:-64]
         if want_stats:
             LAST_STATS.clear()
             LAST_STATS.update(read_status(cx))
     return color, radii, depth, alpha, cx
+
+
+def set_fixed_capacity(cap: Optional[int]) -> None:
+    """None restores the adaptive (polling) policy."""
+    global FIXED_CAPACITY
+    FIXED_CAPACITY = None if cap is None else int(cap)
+    RECENT_CONTEXTS.clear()
+
+
+def overflowed() -> bool:
+    """Deferred check for fixed-capacity mode: did any recent render need more list entries than it was given?"""
+    return any(read_status(cx)["overflow"] for cx in RECENT_CONTEXTS)
 
 
 def read_status(cx: _Context) -> dict:

@@ -189,6 +189,38 @@ def test_culled_lists_are_ordered_subsets(dev):
         assert all(m in it for m in mine), f"tile {t}: culled list is not an ordered subsequence"  # ... and only removes
 
 
+@pytest.mark.parametrize("n", [3000, 20000])
+def test_very_long_tile_lists(dev, n):
+    """n splats stacked on a 2x2-tile patch: exercises the 16k shared-memory sort class (n = 3000) and the in-place
+    global-memory fallback (n = 20000 > 16384), plus multi-batch staging in both composites."""
+    rz = RZ()
+    g = torch.Generator().manual_seed(n)
+    pos = torch.stack([0.12 * (torch.rand(n, generator=g) - 0.5), 0.12 * (torch.rand(n, generator=g) - 0.5),
+                       2.0 + 2.0 * torch.rand(n, generator=g)], 1)
+    assets = {"mean_3d": pos, "scale": 0.01 + 0.02 * torch.rand(n, 3, generator=g),
+              "rotation": torch.nn.functional.normalize(torch.randn(n, 4, generator=g), dim=1),
+              "opacity": 0.02 + 0.05 * torch.rand(n, 1, generator=g), "rgb": torch.rand(n, 3, generator=g)}
+    st_c = kat_settings(W=64, H=48, f=60.0, bg=(0.1, 0.2, 0.3))
+    st_g = kat_settings(W=64, H=48, f=60.0, bg=(0.1, 0.2, 0.3), device=dev, settings_cls=rz.GaussianRasterizationSettings)
+    oc, orad, od, oa, octx = O.forward(st_c, assets["mean_3d"], assets["opacity"], colors_precomp=assets["rgb"],
+                                       scales=assets["scale"], rotations=assets["rotation"])
+    assert octx.ranges()[:, 1].max() - 0 > 0 and (octx.ranges()[:, 1] - octx.ranges()[:, 0]).max() > 0.5 * n
+    gl = {k: v.to(dev).requires_grad_() for k, v in assets.items()}
+    m2 = torch.zeros(n, 3, device=dev, requires_grad=True)
+    color, radii, depth, alpha = rz.GaussianRasterizer(st_g)(means3D=gl["mean_3d"], means2D=m2, opacities=gl["opacity"],
+                                                            colors_precomp=gl["rgb"], scales=gl["scale"],
+                                                            rotations=gl["rotation"])
+    assert np.array_equal(radii.cpu().numpy(), orad)
+    pm, gm = O.fragility(octx)
+    _check("color", color.detach().cpu().numpy(), oc, np.broadcast_to(pm, oc.shape), max_bad_frac=0.2)
+    gi = torch.randn(3, 48, 64, generator=g)
+    (color * gi.to(dev)).sum().backward()
+    og = O.backward(octx, gi.numpy())
+    _check("d_means3D", gl["mean_3d"].grad.cpu().numpy(), og["means3D"], np.broadcast_to(gm[:, None], (n, 3)), max_bad_frac=1.0)
+    _check("d_colors", gl["rgb"].grad.cpu().numpy(), og["colors"], np.broadcast_to(gm[:, None], (n, 3)), max_bad_frac=1.0)
+    _check("d_opacities", gl["opacity"].grad.cpu().numpy(), og["opacities"], np.broadcast_to(gm[:, None], (n, 1)), max_bad_frac=1.0)
+
+
 def test_kats_on_gpu(dev):
     rz = RZ()
     st = kat_settings(device=dev, settings_cls=rz.GaussianRasterizationSettings, bg=(0.25, 0.5, 0.75))
