@@ -14,6 +14,8 @@
 // Accumulator row (12 floats; constants folded in by project_bwd.cu):
 //   q0 = { sum dLdG*(2 gdx A2 + gdy B2), sum dLdG*(2 gdy C2 + gdx B2), sum dLdG*gdx*dx, sum dLdG*gdx*dy }
 //   q1 = { sum dLdG*gdy*dy, sum G*dLdalpha, sum w*g_depth, 0 }      q2 = { sum w*g_r, sum w*g_g, sum w*g_b, 0 }
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b2r {
@@ -243,7 +245,12 @@ __global__ void __launch_bounds__(BWD_THREADS) composite_bwd_kernel(const B2RSce
   if (threadIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&cx.status->consumed_bwd), (unsigned long long)nmax);
 }
 
+int launch_composite_bwd2(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, float* gacc, cudaStream_t st);
+
 int launch_composite_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, float* gacc, cudaStream_t st) {
+  // default: transposed-accumulation variant (composite_bwd2.cu); B2R_BWD_V1=1 selects the butterfly variant below
+  static const bool use_v1 = getenv("B2R_BWD_V1") != nullptr;
+  if (!use_v1) return launch_composite_bwd2(sc, cx, a, gacc, st);
   cudaMemsetAsync(gacc, 0, (size_t)(sc.P > 0 ? sc.P : 1) * 12 * sizeof(float), st);
   ProfScope p(K_COMPOSITE_BWD, st);
   if (a.dL_ddepth || a.dL_dalpha)
