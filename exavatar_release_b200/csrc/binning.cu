@@ -27,11 +27,105 @@ __global__ void __launch_bounds__(256) scatter_kernel(const B2RScene sc, const C
   const int gx = cx.gx;
   uint32_t* cursor = cx.tile_cursor;
   uint2* keys = cx.keys;
-  // same enumeration and the same predicate as the counting pass in project_kernel
-  warp_for_each_kept_tile(aux.z > 0, aux.x & 0xffff, aux.x >> 16, aux.y & 0xffff, aux.y >> 16, g0.x, g0.y, g0.z, g0.w,
-                          g1.x, g1.w, __float_as_uint(g1.z), (uint32_t)i, (sc.flags & B2R_FLAG_NO_TILE_CULL) != 0,
-                          sc.width, sc.height, [&](int tx, int ty, uint32_t depth_bits, uint32_t id) {
-                            const uint32_t pos = atomicAdd(cursor + ty * gx + tx, 1u);
+  const bool no_cull = (sc.flags & B2R_FLAG_NO_TILE_CULL) != 0;
+  const int W = sc.width, H = sc.height;
+  // Same enumeration and the same predicate as the counting pass in project_kernel (warp_for_each_kept_tile), but
+  // written out so that the slot-claiming atomics (ATOMG with a ~700-cycle round trip; 2/3 of this kernel's stall
+  // samples in the first profile) overlap: a lane issues all atomics of a small rect before its first store, and the
+  // cooperative walk of a large rect stores its slots one Gaussian late.
+  auto keep_tile = [&](int tx, int ty, float sx, float sy, float a2, float b2, float c2, float th) {
+    if (no_cull) return true;
+    const float rx0 = (float)(tx * TILE), ry0 = (float)(ty * TILE);
+    const float rx1 = fminf(rx0 + (float)(TILE - 1), (float)(W - 1));
+    const float ry1 = fminf(ry0 + (float)(TILE - 1), (float)(H - 1));
+    return !(region_max_p2(sx, sy, a2, b2, c2, rx0, ry0, rx1, ry1) < th);
+  };
+  const int lane = threadIdx.x & 31;
+  const bool active = aux.z > 0;
+  const int x0 = aux.x & 0xffff, y0 = aux.x >> 16, x1 = aux.y & 0xffff, y1 = aux.y >> 16;
+  const int w = x1 - x0;
+  const int area = active ? w * (y1 - y0) : 0;
+  const uint32_t depth_bits = __float_as_uint(g1.z);
+  constexpr int SMALL = 4;  // must equal warp_for_each_kept_tile's threshold (same pairs either way)
+  constexpr uint32_t NONE = 0xffffffffu;
+  if (area > 0 && area <= SMALL) {
+    uint32_t pos[SMALL];
+#pragma unroll
+    for (int t = 0; t < SMALL; t++) {
+      pos[t] = NONE;
+      if (t < area) {
+        const int ty = y0 + t / w, tx = x0 + t - (t / w) * w;
+        if (keep_tile(tx, ty, g0.x, g0.y, g0.z, g0.w, g1.x, g1.w)) pos[t] = atomicAdd(cursor + ty * gx + tx, 1u);
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < SMALL; t++)
+      if (pos[t] < cap) keys[pos[t]] = make_uint2(depth_bits, (uint32_t)i);  // NONE >= cap always
+  }
+  unsigned mask = __ballot_sync(0xffffffffu, area > SMALL);
+  uint32_t pend_pos = NONE, pend_depth = 0, pend_id = 0;
+  while (mask) {
+    const int src = __ffs(mask) - 1;
+    mask &= mask - 1;
+    const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
+    const int bw = __shfl_sync(0xffffffffu, w, src), barea = __shfl_sync(0xffffffffu, area, src);
+    const float spx = __shfl_sync(0xffffffffu, g0.x, src), spy = __shfl_sync(0xffffffffu, g0.y, src);
+    const float sA = __shfl_sync(0xffffffffu, g0.z, src), sB = __shfl_sync(0xffffffffu, g0.w, src);
+    const float sC = __shfl_sync(0xffffffffu, g1.x, src), sT = __shfl_sync(0xffffffffu, g1.w, src);
+    const uint32_t sd = __shfl_sync(0xffffffffu, depth_bits, src), sid = __shfl_sync(0xffffffffu, (uint32_t)i, src);
+    for (int t = lane; t < barea; t += 32) {
+      const int r = t / bw;
+      const int ty = by0 + r, tx = bx0 + t - r * bw;
+      uint32_t p = NONE;
+      if (keep_tile(tx, ty, spx, spy, sA, sB, sC, sT)) p = atomicAdd(cursor + ty * gx + tx, 1u);
+      if (pend_pos < cap) keys[pend_pos] = make_uint2(pend_depth, pend_id);  // the previous claim has landed by now
+      pend_pos = p; pend_depth = sd; pend_id = sid;
+    }
+  }
+  if (pend_pos < cap) keys[pend_pos] = make_uint2(pend_depth, pend_id);
+}
+
+// K2, aggregated variant (default when the per-tile counters fit in shared memory).  Atomics from different warps to
+// the same global address serialise in L2 (~15 ns each on the hot avatar tiles, which receive thousands), so a CTA
+// claims its slots of a tile with ONE global atomic: (1) count the CTA's pairs per tile in shared memory, (2) one
+// atomicAdd per touched tile reserves a contiguous run of the tile's segment, (3) enumerate again and drop each pair
+// at run base + its rank inside the CTA (shared-memory atomic).  The region test runs twice; it is ~40 instructions.
+__global__ void __launch_bounds__(256) scatter_agg_kernel(const B2RScene sc, const Ctx cx) {
+  extern __shared__ uint32_t s_mem[];
+  uint32_t* s_cnt = s_mem;              // [tiles] pairs of this CTA per tile, then the running rank
+  uint32_t* s_base = s_mem + cx.tiles;  // [tiles] first slot of this CTA's run
+  for (int t = threadIdx.x; t < cx.tiles; t += blockDim.x) s_cnt[t] = 0u;
+  __syncthreads();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int4 aux = make_int4(0, 0, 0, 0);
+  float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+  if (i < sc.P) {
+    aux = cx.aux[i];
+    if (aux.z > 0) {
+      g0 = reinterpret_cast<const float4*>(cx.geom + i)[0];
+      g1 = reinterpret_cast<const float4*>(cx.geom + i)[1];
+    }
+  }
+  const int gx = cx.gx;
+  const bool no_cull = (sc.flags & B2R_FLAG_NO_TILE_CULL) != 0;
+  const int x0 = aux.x & 0xffff, y0 = aux.x >> 16, x1 = aux.y & 0xffff, y1 = aux.y >> 16;
+  warp_for_each_kept_tile(aux.z > 0, x0, y0, x1, y1, g0.x, g0.y, g0.z, g0.w, g1.x, g1.w, 0u, 0u, no_cull, sc.width,
+                          sc.height, [&](int tx, int ty, uint32_t, uint32_t) { atomicAdd(&s_cnt[ty * gx + tx], 1u); });
+  __syncthreads();
+  for (int t = threadIdx.x; t < cx.tiles; t += blockDim.x) {
+    const uint32_t c = s_cnt[t];
+    if (c) {
+      s_base[t] = atomicAdd(cx.tile_cursor + t, c);
+      s_cnt[t] = 0u;
+    }
+  }
+  __syncthreads();
+  const uint64_t cap = cx.dup_capacity;
+  uint2* keys = cx.keys;
+  warp_for_each_kept_tile(aux.z > 0, x0, y0, x1, y1, g0.x, g0.y, g0.z, g0.w, g1.x, g1.w, __float_as_uint(g1.z), (uint32_t)i,
+                          no_cull, sc.width, sc.height, [&](int tx, int ty, uint32_t depth_bits, uint32_t id) {
+                            const int t = ty * gx + tx;
+                            const uint32_t pos = s_base[t] + atomicAdd(&s_cnt[t], 1u);
                             if (pos < cap) keys[pos] = make_uint2(depth_bits, id);
                           });
 }
@@ -257,7 +351,18 @@ constexpr int SORT_LARGE = 16384;  // 512 threads, 201 KB of shared memory: one 
 int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t st) {
   // the two-phase entry re-derives ranges and cursors for the capacity the caller finally chose
   if (rescan) launch_tile_scan(cx, st);
-  if (sc.P > 0) { ProfScope p(K_SCATTER, st); scatter_kernel<<<(sc.P + 255) / 256, 256, 0, st>>>(sc, cx); }
+  if (sc.P > 0) {
+    ProfScope p(K_SCATTER, st);
+    const size_t smem = (size_t)cx.tiles * 8;
+    // worth it while the per-CTA zero / flush sweeps over the tile table stay small (measured: 1024 tiles 1.3-1.6x
+    // faster, 8160 tiles 2x slower than direct atomics)
+    if (cx.tiles <= 4096) {
+      cudaFuncSetAttribute(scatter_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
+      scatter_agg_kernel<<<(sc.P + 255) / 256, 256, smem, st>>>(sc, cx);
+    } else {
+      scatter_kernel<<<(sc.P + 255) / 256, 256, 0, st>>>(sc, cx);
+    }
+  }
   static int sms = 0;
   if (sms == 0) {
     int dev = 0;

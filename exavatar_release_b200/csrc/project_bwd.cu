@@ -205,6 +205,9 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
     }
   }
 
+  if (visible && out.densify_grad_accum) out.densify_grad_accum[i] += sqrtf(dm2[0] * dm2[0] + dm2[1] * dm2[1]);
+  if (visible && out.densify_count) out.densify_count[i] += 1.f;
+  if (visible && out.densify_radius_max) out.densify_radius_max[i] = fmaxf(out.densify_radius_max[i], (float)aux.z);
   auto put3 = [&](float* base, const float* v) {
     if (!base) return;
     float* d = base + 3 * (size_t)i;

@@ -61,12 +61,17 @@ class FramePlan:
             L.check(self.lib.b2r_forward(C.byref(sc), C.byref(self.ws), C.byref(self.out), st), "b2r_forward")
 
     def backward(self, sc, g_color: torch.Tensor, grads: Dict[str, Optional[torch.Tensor]], accumulate: bool = False,
-                 g_depth: Optional[torch.Tensor] = None, g_alpha: Optional[torch.Tensor] = None) -> None:
-        """grads keys: means3D, means2D, shs, colors, opacities, scales, rotations, cov3D (missing -> not written)."""
+                 g_depth: Optional[torch.Tensor] = None, g_alpha: Optional[torch.Tensor] = None,
+                 densify: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        """grads keys: means3D, means2D, shs, colors, opacities, scales, rotations, cov3D (missing -> not written).
+        densify (optional): {'grad_accum', 'count', 'radius_max'} fp32 (P) tensors updated in place by the backward
+        projection kernel -- ExAvatar's `track_stats` + `radius_max` update (module.py:155-157, model.py:283-285)."""
         a = L.B2RBackwardArgs(_ptr(g_color), _ptr(g_depth), _ptr(g_alpha), _ptr(grads.get("means3D")),
                               _ptr(grads.get("means2D")), _ptr(grads.get("shs")), _ptr(grads.get("colors")),
                               _ptr(grads.get("opacities")), _ptr(grads.get("scales")), _ptr(grads.get("rotations")),
-                              _ptr(grads.get("cov3D")), L.B2R_BWD_ACCUMULATE if accumulate else 0, 0)
+                              _ptr(grads.get("cov3D")), L.B2R_BWD_ACCUMULATE if accumulate else 0, 0,
+                              _ptr((densify or {}).get("grad_accum")), _ptr((densify or {}).get("count")),
+                              _ptr((densify or {}).get("radius_max")))
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream(self.device).cuda_stream
             L.check(self.lib.b2r_backward(C.byref(sc), C.byref(self.ws), C.byref(a), self.bwd_scratch.data_ptr(),

@@ -117,6 +117,12 @@ typedef struct B2RBackwardArgs {
   uint32_t flags;       /* B2R_BWD_ACCUMULATE: outputs += gradient instead of outputs = gradient, so the frames a rank
                            renders in one step sum into a single bucket that is all-reduced once */
   uint32_t reserved;
+  /* Optional fused densification bookkeeping, each (P) or NULL, updated IN PLACE for Gaussians
+   * with radii > 0 exactly as ExAvatar does after backward (avatar/common/nets/module.py:155-157,
+   * avatar/main/model.py:283-285):  grad_accum += ||dL/dmeans2D.xy||,  count += 1,  radius_max = max(radius_max, radii). */
+  float* densify_grad_accum;
+  float* densify_count;
+  float* densify_radius_max;
 } B2RBackwardArgs;
 #define B2R_BWD_ACCUMULATE 1u
 

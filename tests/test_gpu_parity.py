@@ -428,3 +428,31 @@ def test_renderer_end_to_end_on_gpu(dev):
     assert out["img"].shape == (3, 96, 128) and out["radius"].shape == (P,) and out["is_vis"].dtype == torch.bool
     out["img"].mean().backward()
     assert out["mean_2d"].grad.shape == (P, 3) and float(out["mean_2d"].grad.abs().sum()) > 0
+
+
+def test_fused_densification_stats_match_reference_bookkeeping(dev):
+    """K6 updates xyz_grad_accum / track_cnt / radius_max exactly as module.py:155-157 + model.py:283-285."""
+    from exavatar_release_b200.plan import FramePlan, grad_bucket
+    rz = RZ()
+    wl = WORKLOADS["T1"]
+    a = {k: v.to(dev) for k, v in make_assets("T1", seed=0).items()}
+    P = a["mean_3d"].shape[0]
+    plan = FramePlan(P, wl.width, wl.height, 1_000_000, dev)
+    fused = {"grad_accum": torch.zeros(P, device=dev), "count": torch.zeros(P, device=dev),
+             "radius_max": torch.zeros(P, device=dev)}
+    ref_accum, ref_cnt, ref_rmax = torch.zeros(P, 1, device=dev), torch.zeros(P, 1, device=dev), torch.zeros(P, device=dev)
+    for i, yaw in enumerate((-12.0, 0.0, 14.0)):
+        st = workload_settings("T1", yaw=yaw, device=dev, settings_cls=rz.GaussianRasterizationSettings)
+        sc = plan.scene(i, st, a)
+        flat, views = grad_bucket(P, dev)
+        plan.forward(sc)
+        plan.backward(sc, make_grad_image("T1", i).to(dev), views, densify=fused)
+        torch.cuda.synchronize()
+        # the reference's own statements, on the tensors the rasteriser returned
+        is_vis = plan.radii > 0
+        ref_rmax[is_vis] = torch.maximum(ref_rmax[is_vis], plan.radii[is_vis].float())
+        ref_accum[is_vis, :] += torch.norm(views["means2D"][is_vis, :2], dim=1, keepdim=True)
+        ref_cnt[is_vis, :] += 1
+    assert torch.equal(fused["count"], ref_cnt[:, 0]) and torch.equal(fused["radius_max"], ref_rmax)
+    assert torch.allclose(fused["grad_accum"], ref_accum[:, 0], rtol=1e-5, atol=1e-6 * float(ref_accum.max()))
+    assert float(fused["count"].max()) == 3.0 and float(fused["grad_accum"].max()) > 0
