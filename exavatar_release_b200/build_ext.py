@@ -37,7 +37,8 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
-    cmd = [nvcc, *NVCC_FLAGS, *(["-Xptxas", "-v"] if ptxas_info else []), "-o", LIB, *sources()]
+    extra = os.environ.get("B2R_NVCC_EXTRA", "").split()  # e.g. -DB2_DRAIN_UNROLL=8 for tuning experiments
+    cmd = [nvcc, *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if ptxas_info else []), "-o", LIB, *sources()]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)

@@ -356,7 +356,7 @@ int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t 
     const size_t smem = (size_t)cx.tiles * 8;
     // worth it while the per-CTA zero / flush sweeps over the tile table stay small (measured: 1024 tiles 1.3-1.6x
     // faster, 8160 tiles 2x slower than direct atomics)
-    if (cx.tiles <= 4096) {
+    if (cx.tiles <= 2048) {
       cudaFuncSetAttribute(scatter_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
       scatter_agg_kernel<<<(sc.P + 255) / 256, 256, smem, st>>>(sc, cx);
     } else {

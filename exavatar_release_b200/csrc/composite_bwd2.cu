@@ -24,7 +24,13 @@ namespace b2r {
 constexpr int B2_THREADS = 64;
 constexpr int B2_BATCH = 64;
 constexpr int B2_PER_THREAD = B2_BATCH / B2_THREADS;
-constexpr int B2_QUEUE = 32;
+#ifndef B2_QUEUE_DEPTH
+#define B2_QUEUE_DEPTH 16
+#endif
+constexpr int B2_QUEUE = B2_QUEUE_DEPTH;  // 32 or 16
+#ifndef B2_DRAIN_UNROLL
+#define B2_DRAIN_UNROLL 32
+#endif
 
 struct B2Stage {
   float4 a[B2_BATCH];
@@ -86,16 +92,25 @@ __global__ void __launch_bounds__(B2_THREADS) composite_bwd2_kernel(const B2RSce
   float acd = 0.f, lcd = 0.f, aca = 0.f;
   int qpos = 0;  // warp-uniform
 
-  // phase B: lane l owns queued splat l
+  // phase B: with a 32-deep queue lane l owns queued splat l and walks all 32 pixels; with a 16-deep queue (half the
+  // transposition buffer, more CTAs per SM) lanes l and l+16 share splat l, walk 16 pixels each and are combined
+  // with one shuffle per sum
   auto drain = [&](const int count) {
+    constexpr int HALVES = 32 / B2_QUEUE;
+    constexpr int PIX = 32 / HALVES;
     __syncwarp();
-    if (lane < count) {
-      const float4 m0 = qm0[warp][lane];
-      const float4 m1 = qm1[warp][lane];
-      float Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, Sq = 0.f, Sr = 0.f, Sg = 0.f, Sb = 0.f, Sd = 0.f;
-#pragma unroll
-      for (int p = 0; p < 32; p++) {
-        const float2 t = tb[warp][lane][p];
+    const int h = lane % B2_QUEUE, half = lane / B2_QUEUE;
+    const bool live = h < count;
+    float Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, Sq = 0.f, Sr = 0.f, Sg = 0.f, Sb = 0.f, Sd = 0.f;
+    float4 m0 = make_float4(0.f, 0.f, 1.f, 0.f), m1 = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (live) {
+      m0 = qm0[warp][h];
+      m1 = qm1[warp][h];
+      constexpr int kUnroll = B2_DRAIN_UNROLL < PIX ? B2_DRAIN_UNROLL : PIX;
+#pragma unroll kUnroll
+      for (int k = 0; k < PIX; k++) {
+        const int p = half * PIX + k;
+        const float2 t = tb[warp][h][p];
         const float4 g = gpix[warp][p];
         const float dx = m0.x - (float)(p & 7), dy = m0.y - (float)(p >> 3);
         const float hx = t.x * dx, hy = t.x * dy;
@@ -110,6 +125,20 @@ __global__ void __launch_bounds__(B2_THREADS) composite_bwd2_kernel(const B2RSce
         Sb = fmaf(t.y, g.z, Sb);
         if (HAS_DA) Sd = fmaf(t.y, g.w, Sd);
       }
+    }
+    if (HALVES == 2) {
+      Sx += __shfl_xor_sync(0xffffffffu, Sx, 16);
+      Sy += __shfl_xor_sync(0xffffffffu, Sy, 16);
+      Sxx += __shfl_xor_sync(0xffffffffu, Sxx, 16);
+      Sxy += __shfl_xor_sync(0xffffffffu, Sxy, 16);
+      Syy += __shfl_xor_sync(0xffffffffu, Syy, 16);
+      Sq += __shfl_xor_sync(0xffffffffu, Sq, 16);
+      Sr += __shfl_xor_sync(0xffffffffu, Sr, 16);
+      Sg += __shfl_xor_sync(0xffffffffu, Sg, 16);
+      Sb += __shfl_xor_sync(0xffffffffu, Sb, 16);
+      if (HAS_DA) Sd += __shfl_xor_sync(0xffffffffu, Sd, 16);
+    }
+    if (live && half == 0) {
       // accumulator row convention of project_bwd.cu
       float* dst = gacc + (size_t)__float_as_uint(m0.w) * 12;
       red_add_v4(dst, 2.f * m1.x * Sx + m1.y * Sy, 2.f * m1.z * Sy + m1.y * Sx, Sxx, Sxy);
@@ -154,20 +183,33 @@ __global__ void __launch_bounds__(B2_THREADS) composite_bwd2_kernel(const B2RSce
           hit = !(region_max_p2(a.x, a.y, a.z, a.w, bb.x, rx0, ry0, rx1, ry1) < bb.w);
         }
         unsigned mask = __ballot_sync(0xffffffffu, hit);
+        // Two survivors per trip: their exponent evaluations (shared loads, MUFU) are independent and overlap; only the
+        // short blend-state recurrence is serial.  The longest lists bound this kernel by per-warp latency, not issue.
         while (mask) {
-          const int k = 31 - __clz(mask);
-          mask &= ~(1u << k);
-          const int j = c0 + k;
-          const float4 a = s.a[j];
-          const float4 bb = s.b[j];
-          const float dx = a.x - pxf, dy = a.y - pyf;
-          const float p2 = a.z * dx * dx + bb.x * dy * dy + a.w * dx * dy;
-          const float G = ex2_approx(p2);
-          const float alpha = fminf(K_ALPHA_MAX, bb.y * G);
-          const bool valid = (b * B2_BATCH + j < my_n) && (p2 <= 0.f) && (alpha >= K_ALPHA_MIN);
-          if (!__any_sync(0xffffffffu, valid)) continue;
+          const int k0 = 31 - __clz(mask);
+          mask &= ~(1u << k0);
+          const bool two = mask != 0u;
+          const int k1 = two ? 31 - __clz(mask) : k0;
+          if (two) mask &= ~(1u << k1);
+          const int j0 = c0 + k0, j1 = c0 + k1;
+          const float4 a0 = s.a[j0], b0 = s.b[j0], col0 = s.c[j0];
+          const float4 a1 = s.a[j1], b1 = s.b[j1], col1 = s.c[j1];
+          const float dx0 = a0.x - pxf, dy0 = a0.y - pyf, dx1 = a1.x - pxf, dy1 = a1.y - pyf;
+          const float p20 = a0.z * dx0 * dx0 + b0.x * dy0 * dy0 + a0.w * dx0 * dy0;
+          const float p21 = a1.z * dx1 * dx1 + b1.x * dy1 * dy1 + a1.w * dx1 * dy1;
+          const float G0 = ex2_approx(p20), G1 = ex2_approx(p21);
+          const float al0 = fminf(K_ALPHA_MAX, b0.y * G0), al1 = fminf(K_ALPHA_MAX, b1.y * G1);
+          const bool v0 = (b * B2_BATCH + j0 < my_n) && (p20 <= 0.f) && (al0 >= K_ALPHA_MIN);
+          const bool v1 = two && (b * B2_BATCH + j1 < my_n) && (p21 <= 0.f) && (al1 >= K_ALPHA_MIN);
+          const bool any0 = __any_sync(0xffffffffu, v0), any1 = __any_sync(0xffffffffu, v1);
+#pragma unroll
+          for (int u = 0; u < 2; u++) {
+          if (!(u == 0 ? any0 : any1)) continue;  // warp-uniform
+          const float4 a = u == 0 ? a0 : a1, bb = u == 0 ? b0 : b1, col = u == 0 ? col0 : col1;
+          const float G = u == 0 ? G0 : G1, alpha = u == 0 ? al0 : al1;
+          const bool valid = u == 0 ? v0 : v1;
+          const int j = u == 0 ? j0 : j1;
           // ---- phase A: branch-free state replay; a skipped splat enters with alpha = 0 (identity) ----
-          const float4 col = s.c[j];
           const float ae = valid ? alpha : 0.f;
           const float Ge = valid ? G : 0.f;
           const float rcp = __fdividef(1.f, 1.f - ae);
@@ -196,6 +238,7 @@ __global__ void __launch_bounds__(B2_THREADS) composite_bwd2_kernel(const B2RSce
             drain(B2_QUEUE);
             qpos = 0;
           }
+          }  // u
         }
       }
     }

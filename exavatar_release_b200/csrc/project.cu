@@ -254,7 +254,7 @@ int launch_project(const B2RScene& sc, const Ctx& cx, int32_t* radii, cudaStream
   if (sc.P > 0) {
     ProfScope p(K_PROJECT, st);
     const size_t smem = (size_t)cx.tiles * 4;
-    const int aggregate = cx.tiles <= 4096;  // beyond that the per-CTA sweeps over the tile table cost more than they save
+    const int aggregate = cx.tiles <= 2048;  // beyond that the per-CTA sweeps over the tile table cost more than they save
     project_kernel<<<(sc.P + 255) / 256, 256, aggregate ? smem : 0, st>>>(sc, cx, radii, aggregate);
   }
   { ProfScope p(K_TILE_SCAN, st); tile_scan_kernel<<<1, 1024, 0, st>>>(cx); }
