@@ -231,12 +231,23 @@ __device__ __forceinline__ void radix_sort_tile(const uint2* __restrict__ src, u
     }
     __syncthreads();
     // scan: hist[w][d] <- first output slot of (digit d, warp w)
+    // each of the first 256 / DPT threads owns DPT consecutive digits (DPT = 2 for the 128-thread class)
+    constexpr int DPT = THREADS >= 256 ? 1 : 256 / THREADS;
+    constexpr int SCAN_THREADS = 256 / DPT;
+    uint32_t tot[DPT];
     uint32_t total = 0;
-    if (tid < 256) {
-      for (int w = 0; w < W; w++) {
-        const uint32_t t = hist[w * 256 + tid];
-        hist[w * 256 + tid] = (uint16_t)total;
-        total += t;
+    if (tid < SCAN_THREADS) {
+#pragma unroll
+      for (int r = 0; r < DPT; r++) {
+        const int d = tid * DPT + r;
+        uint32_t run = 0;
+        for (int w = 0; w < W; w++) {
+          const uint32_t t = hist[w * 256 + d];
+          hist[w * 256 + d] = (uint16_t)run;
+          run += t;
+        }
+        tot[r] = run;
+        total += run;
       }
     }
     uint32_t incl = total;
@@ -245,12 +256,17 @@ __device__ __forceinline__ void radix_sort_tile(const uint2* __restrict__ src, u
       const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
       if (lane >= o) incl += v;
     }
-    if (tid < 256 && lane == 31) misc[2 + warp] = incl;
+    if (tid < SCAN_THREADS && lane == 31) misc[2 + warp] = incl;
     __syncthreads();
-    if (tid < 256) {
+    if (tid < SCAN_THREADS) {
       uint32_t base = incl - total;
       for (int w = 0; w < warp; w++) base += misc[2 + w];
-      for (int w = 0; w < W; w++) hist[w * 256 + tid] = (uint16_t)(hist[w * 256 + tid] + base);
+#pragma unroll
+      for (int r = 0; r < DPT; r++) {
+        const int d = tid * DPT + r;
+        for (int w = 0; w < W; w++) hist[w * 256 + d] = (uint16_t)(hist[w * 256 + d] + base);
+        base += tot[r];
+      }
     }
     __syncthreads();
     // pass 2: stable scatter
@@ -370,11 +386,15 @@ int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-  constexpr size_t small_bytes = RadixSmem<SORT_SMALL, 256>::bytes, large_bytes = RadixSmem<SORT_LARGE, 512>::bytes;
+#ifndef B2_SORT_SMALL_THREADS
+#define B2_SORT_SMALL_THREADS 256
+#endif
+  constexpr int ST = B2_SORT_SMALL_THREADS;
+  constexpr size_t small_bytes = RadixSmem<SORT_SMALL, ST>::bytes, large_bytes = RadixSmem<SORT_LARGE, 512>::bytes;
   cudaFuncSetAttribute(sort_tiles_kernel<SORT_LARGE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)large_bytes);
   {
     ProfScope p(K_SORT_SMALL, st);
-    sort_tiles_kernel<SORT_SMALL, 256><<<cx.tiles, 256, small_bytes, st>>>(cx, 0, SORT_SMALL);
+    sort_tiles_kernel<SORT_SMALL, ST><<<cx.tiles, ST, small_bytes, st>>>(cx, 0, SORT_SMALL);
   }
   {
     ProfScope p(K_SORT_LARGE, st);
