@@ -49,6 +49,7 @@ def parse():
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--workload", default="C2", choices=[k for k in WORKLOADS if k.startswith("C")])
     ap.add_argument("--frames", type=int, default=8, help="frames per rank per step")
+    ap.add_argument("--lanes", type=int, default=4, help="frames in flight per rank (CUDA streams; 1 = serial)")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -194,7 +195,7 @@ def run_b200(args):
     import torch.distributed as dist
     from exavatar_release_b200 import _lib as L
     from exavatar_release_b200 import rasterizer as RZ
-    from exavatar_release_b200.plan import FramePlan, grad_bucket
+    from exavatar_release_b200.plan import FrameLanes
     from exavatar_release_b200.renderer import GaussianRenderer, render_settings
 
     rank = int(os.environ.get("RANK", "0"))
@@ -242,15 +243,14 @@ def run_b200(args):
             dups.append(RZ._state(dev).predicted[(P, Wd, H)])
     cap = int(max(dups) * 1.1) + 4096
 
-    plan = FramePlan(P, Wd, H, cap, dev, sh_coeffs=M)
-    scenes = [plan.scene(f, settings[f], assets) for f in range(F)]
-    bucket, views = grad_bucket(P, dev, M)
+    S = max(1, min(args.lanes, F))
+    lanes = FrameLanes(S, P, Wd, H, cap, dev, sh_coeffs=M)
+    plan = lanes.plans[0]
+    scenes = [lanes.scene(f, settings[f], assets) for f in range(F)]
+    bucket, views = lanes.bucket, lanes.lane_views[0]
 
     def step_body():
-        for f in range(F):
-            plan.forward(scenes[f])
-            if wl.backward:
-                plan.backward(scenes[f], gimgs[f], views, accumulate=(f > 0))
+        lanes.step(scenes, gimgs, backward=wl.backward)
 
     graph = None
     if not args.no_graph:
@@ -261,8 +261,10 @@ def run_b200(args):
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
         graph = torch.cuda.CUDAGraph()
+        l0 = lib.b2r_launch_count()
         with torch.cuda.graph(graph):
             step_body()
+        launches_per_step = lib.b2r_launch_count() - l0  # kernels of this library recorded into the graph
 
     def step():
         if graph is not None:
@@ -301,11 +303,10 @@ def run_b200(args):
     clocks = ClockSampler(local) if rank == 0 else None
     ms_total, wall, launches_eager = timed(step, K)
     clk = clocks.stop() if clocks else None
-    st_last = plan.status()
+    st_last = lanes.status()
     if st_last["overflow"]:
         raise SystemExit("bench.py: duplicate capacity overflowed; results invalid")
-    kernels_per_frame = 7 + (2 if wl.backward else 0)
-    launches = launches_eager if graph is None else K * F * kernels_per_frame
+    launches = launches_eager if graph is None else K * launches_per_step
     fps = world * F * K / (ms_total * 1e-3)
 
     # ---- leg 2: per-kernel durations (same step, eager, in-library events) ----
@@ -379,6 +380,7 @@ def run_b200(args):
         # copies of frame f+1 / f-1 run on forked streams beside frame f's kernels.  Host cost per step: one launch.
         RZ.set_fixed_capacity(cap)
         h2d_s, d2h_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        lane_s = [torch.cuda.Stream(dev) for _ in range(S)] if S > 1 else None
         keep_alive = []  # nothing allocated inside the capture may be recycled across the forked streams
 
         def upload(f, cur):
@@ -391,42 +393,56 @@ def run_b200(args):
             keep_alive.append((lv, tgt))
             return lv, tgt, ev
 
+        def e2e_frame(f, lv, tgt):
+            lv = {k: v.requires_grad_(wl.backward) for k, v in lv.items()}
+            if use_sh:
+                img, _, m2 = public_frame(f, leaves=lv)
+            else:
+                o = renderer(lv, (H, Wd), cams[f], bg, raster_settings=settings[f])
+                img, m2 = o["img"], o["mean_2d"]
+            if wl.backward:
+                loss = (img - tgt).abs().mean()
+                loss.backward()
+                outs = [(host_loss[f:f + 1], loss.detach().reshape(1)), (host_m2, m2.grad)]
+                outs += [(host_grads[k], lv[k].grad) for k in host_grads]
+            else:
+                outs = [(host_img, img.detach())]
+            keep_alive.append((lv, img, m2, outs))
+            return outs
+
         def e2e_body():
             cur = torch.cuda.current_stream(dev)
+            if lane_s:
+                for ls in lane_s:
+                    ls.wait_stream(cur)
+            d2h_s.wait_stream(cur)
             nxt = upload(0, cur)
             for f in range(F):
                 lv, tgt, ev = nxt
                 if f + 1 < F:
                     nxt = upload(f + 1, cur)
-                cur.wait_event(ev)
-                lv = {k: v.requires_grad_(wl.backward) for k, v in lv.items()}
-                if use_sh:
-                    img, _, m2 = public_frame(f, leaves=lv)
-                else:
-                    o = renderer(lv, (H, Wd), cams[f], bg, raster_settings=settings[f])
-                    img, m2 = o["img"], o["mean_2d"]
-                if wl.backward:
-                    loss = (img - tgt).abs().mean()
-                    loss.backward()
-                    outs = [(host_loss[f:f + 1], loss.detach().reshape(1)), (host_m2, m2.grad)]
-                    outs += [(host_grads[k], lv[k].grad) for k in host_grads]
-                else:
-                    outs = [(host_img, img.detach())]
-                keep_alive.append((lv, img, m2, outs))
-                done = torch.cuda.Event()
-                done.record(cur)
+                fs = lane_s[f % S] if lane_s else cur  # frame f runs on lane f mod S
+                fs.wait_event(ev)
+                with torch.cuda.stream(fs):
+                    outs = e2e_frame(f, lv, tgt)
+                    done = torch.cuda.Event()
+                    done.record(fs)
                 with torch.cuda.stream(d2h_s):
                     d2h_s.wait_event(done)
                     for dst, src in outs:
                         dst.copy_(src, non_blocking=True)
             cur.wait_stream(d2h_s)  # the step ends when its last result is in host memory (joins the forked streams)
             cur.wait_stream(h2d_s)
+            if lane_s:
+                for ls in lane_s:
+                    cur.wait_stream(ls)
 
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
         with torch.cuda.stream(side):
             for _ in range(2):
                 e2e_body()
+                torch.cuda.synchronize(dev)  # buffers cross streams: do not recycle them while a lane may still read
                 keep_alive.clear()
         torch.cuda.current_stream(dev).wait_stream(side)
         torch.cuda.synchronize(dev)
@@ -446,6 +462,7 @@ def run_b200(args):
                 e2e_graph.replay()
             else:
                 e2e_body()
+                torch.cuda.synchronize(dev)
                 keep_alive.clear()
             if world > 1 and wl.backward:
                 dist.all_reduce(bucket)  # same collective as the device-resident leg
@@ -481,7 +498,7 @@ def run_b200(args):
         line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
                 "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
                 "dtype": "f32", "data": "synthetic",
-                "config": config_dict(args, wl, {"cuda_graph": graph is not None, "dup_capacity": cap,
+                "config": config_dict(args, wl, {"cuda_graph": graph is not None, "dup_capacity": cap, "lanes": S,
                                                  "frames_per_rank_per_step": F}),
                 "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
                 "wall_s_timed_region": wall}

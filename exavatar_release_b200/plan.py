@@ -87,10 +87,67 @@ class FramePlan:
 
 def grad_bucket(P: int, device, sh_coeffs: int = 0):
     """One flat fp32 buffer holding every per-Gaussian gradient, plus named views into it."""
+    per = 3 + 3 + 1 + 3 + 4 + (3 * sh_coeffs if sh_coeffs > 0 else 3)
+    return _views_of(torch.zeros(per * P, dtype=torch.float32, device=device), P, sh_coeffs)
+
+
+class FrameLanes:
+    """S concurrent `FramePlan`s ("lanes"), each on its own CUDA stream with its own workspace and gradient bucket.
+
+    Frames of a training batch are independent (avatar/main/model.py:81 loops over them), and at
+    ExAvatar's sizes a single frame cannot fill a B200: the scan / sort kernels are latency-bound single-wave launches
+    and the composites end in a tail of long tile lists.  Running frame f on lane f mod S lets the hardware fill those
+    holes with another frame's kernels.  The lanes fork from and join back into the caller's current stream, so the
+    whole step is still one CUDA-graph capture.  Gradients of the frames of one lane are summed inside the backward
+    projection kernel (`accumulate`); the S lane buckets are then added in a fixed order (deterministic result) into
+    `bucket`, the tensor that is all-reduced once per step.
+    """
+
+    def __init__(self, lanes: int, P: int, width: int, height: int, dup_capacity: int, device, sh_coeffs: int = 0):
+        self.S = max(1, int(lanes))
+        self.device = torch.device(device)
+        self.plans = [FramePlan(P, width, height, dup_capacity, device, sh_coeffs) for _ in range(self.S)]
+        self.streams = [torch.cuda.Stream(self.device) for _ in range(self.S)]
+        flat0, _ = grad_bucket(P, device, sh_coeffs)
+        self.lane_flat = torch.zeros(self.S, flat0.numel(), dtype=torch.float32, device=device)
+        self.lane_views = []
+        for s in range(self.S):
+            _, v = _views_of(self.lane_flat[s], P, sh_coeffs)
+            self.lane_views.append(v)
+        self.bucket = self.lane_flat[0] if self.S == 1 else flat0
+        _, self.views = _views_of(self.bucket, P, sh_coeffs)
+
+    def scene(self, key, settings, assets, flags: int = 0):
+        return self.plans[0].scene(key, settings, assets, flags)
+
+    def step(self, scenes, g_colors, backward: bool = True) -> None:
+        """Forward (+ backward) of every frame in `scenes`; on return (stream order) `bucket` holds the summed gradients."""
+        cur = torch.cuda.current_stream(self.device)
+        F = len(scenes)
+        for s in range(self.S):
+            st = self.streams[s]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                plan = self.plans[s]
+                for j, f in enumerate(range(s, F, self.S)):
+                    plan.forward(scenes[f])
+                    if backward:
+                        plan.backward(scenes[f], g_colors[f], self.lane_views[s], accumulate=(j > 0))
+        for st in self.streams:
+            cur.wait_stream(st)
+        if backward and self.S > 1:
+            torch.sum(self.lane_flat[: min(self.S, F)], dim=0, out=self.bucket)
+
+    def status(self) -> dict:
+        sts = [p.status() for p in self.plans]
+        out = dict(sts[0])
+        out["overflow"] = int(any(s["overflow"] for s in sts))
+        return out
+
+
+def _views_of(flat: torch.Tensor, P: int, sh_coeffs: int = 0):
     widths = [("means3D", 3), ("means2D", 3), ("opacities", 1), ("scales", 3), ("rotations", 4)]
     widths.append(("shs", 3 * sh_coeffs) if sh_coeffs > 0 else ("colors", 3))
-    total = sum(w for _, w in widths) * P
-    flat = torch.zeros(total, dtype=torch.float32, device=device)
     views, o = {}, 0
     for name, w in widths:
         views[name] = flat[o:o + w * P].view(P, w) if name != "shs" else flat[o:o + w * P].view(P, sh_coeffs, 3)

@@ -419,6 +419,48 @@ def test_cuda_graph_replay_matches_eager(dev):
     assert torch.allclose(flat, eager_grad, rtol=1e-4, atol=1e-5 * float(eager_grad.abs().max()))
 
 
+def test_frame_lanes_match_serial_accumulation(dev):
+    """FrameLanes (frames in flight on S streams, per-lane buckets, fixed-order sum) == one plan run serially; also
+    inside a CUDA graph capture (the lanes fork from / join into the capturing stream)."""
+    from exavatar_release_b200.plan import FrameLanes, FramePlan, grad_bucket
+    rz = RZ()
+    wl = WORKLOADS["T1"]
+    a = {k: v.to(dev) for k, v in make_assets("T1", seed=0).items()}
+    P = a["mean_3d"].shape[0]
+    yaws = (-15.0, -5.0, 0.0, 7.0, 14.0)
+    sts = [workload_settings("T1", yaw=y, device=dev, settings_cls=rz.GaussianRasterizationSettings) for y in yaws]
+    gis = [make_grad_image("T1", s).to(dev) for s in range(len(yaws))]
+    plan = FramePlan(P, wl.width, wl.height, 1_000_000, dev)
+    scenes = [plan.scene(i, sts[i], a) for i in range(len(yaws))]
+    flat, views = grad_bucket(P, dev)
+    for i, sc in enumerate(scenes):
+        plan.forward(sc)
+        plan.backward(sc, gis[i], views, accumulate=(i > 0))
+    torch.cuda.synchronize()
+    tol = dict(rtol=1e-4, atol=2e-6 * float(flat.abs().max()))
+    for S in (1, 2, 3, 8):
+        lanes = FrameLanes(S, P, wl.width, wl.height, 1_000_000, dev)
+        lanes.step(scenes, gis)
+        torch.cuda.synchronize()
+        assert torch.allclose(lanes.bucket, flat, **tol), S
+        assert lanes.status()["overflow"] == 0
+    lanes = FrameLanes(3, P, wl.width, wl.height, 1_000_000, dev)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        lanes.step(scenes, gis)
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        lanes.step(scenes, gis)
+    lanes.bucket.zero_()
+    lanes.lane_flat.zero_()
+    g.replay()
+    torch.cuda.synchronize()
+    assert torch.allclose(lanes.bucket, flat, **tol)
+
+
 def test_renderer_end_to_end_on_gpu(dev):
     from exavatar_release_b200 import GaussianRenderer
     from exavatar_release_b200.camera import look_at_cam_param
