@@ -8,6 +8,7 @@ namespace {
 int validate_scene(const B2RScene* sc) {
   if (!sc) return B2R_E_INVALID;
   if (sc->P < 0 || sc->width <= 0 || sc->height <= 0) return B2R_E_INVALID;
+  if (sc->P >= (1 << 29)) return B2R_E_INVALID;  // the splat record carries id in 29 bits (common.cuh Geom)
   if (sc->width > 65535 * TILE || sc->height > 32767 * TILE) return B2R_E_INVALID;
   if (!(sc->tanfovx > 0.f) || !(sc->tanfovy > 0.f)) return B2R_E_INVALID;
   if (!sc->bg || !sc->viewmatrix || !sc->projmatrix || !sc->campos) return B2R_E_INVALID;

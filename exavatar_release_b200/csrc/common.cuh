@@ -31,7 +31,7 @@ __host__ __device__ inline size_t align_up(size_t v) { return (v + ALIGN - 1) / 
 struct Geom {  // 48 bytes per Gaussian, three 16-byte vectors
   float4 g0;   // px, py, A2, B2
   float4 g1;   // C2, opacity, depth, thr2
-  float4 g2;   // r, g, b, bits (SH clamp mask in bits 0..2)
+  float4 g2;   // r, g, b, id | SH clamp mask << 29 (uint bits)
 };
 static_assert(sizeof(Geom) == 48, "Geom must be 48 bytes");
 

@@ -1,7 +1,7 @@
 // composite_bwd2.cu -- K5 (default variant): backward alpha-composite (App. A.4) with a transposed accumulation phase.
 //
 // Same work decomposition as composite_fwd.cu (one 64-thread CTA per 8x8 quarter tile, longest list first, cp.async
-// staging, 8x4 sub-tile culling, back to front).  What differs from composite_bwd.cu is how the 32 pixels of a warp
+// staging, 8x4 sub-tile culling, back to front).  What differs from the first (butterfly-reduction) backward is how the 32 pixels of a warp
 // are summed into per-splat gradients:
 //
 //   phase A (lanes = pixels)  for every surviving splat the warp replays the blend state of its 32 pixels and writes

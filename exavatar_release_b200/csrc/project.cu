@@ -120,7 +120,7 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
           else thr2 = -log2f(255.f * o) - CULL_MARGIN2;
           g.g0 = make_float4(px, py, A2, B2);
           g.g1 = make_float4(C2, o, pv.z, thr2);
-          g.g2 = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float(bits));
+          g.g2 = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float((bits << 29) | (uint32_t)i));  // id rides with the record
           aux = make_int4(x0 | (y0 << 16), x1 | (y1 << 16), radius, (x1 - x0) * (y1 - y0));
         }
       }

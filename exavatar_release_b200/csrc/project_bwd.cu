@@ -39,7 +39,7 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
     dop = q1.y;
     const float ddep = q1.z;
     dcol[0] = q2.x; dcol[1] = q2.y; dcol[2] = q2.z;
-    clamp_bits = __float_as_uint(reinterpret_cast<const float4*>(cx.geom + i)[2].w);
+    clamp_bits = __float_as_uint(reinterpret_cast<const float4*>(cx.geom + i)[2].w) >> 29;
 
     p = make_float3(__ldg(sc.means3D + 3 * (size_t)i), __ldg(sc.means3D + 3 * (size_t)i + 1),
                     __ldg(sc.means3D + 3 * (size_t)i + 2));
