@@ -53,6 +53,11 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--e2e-upload", default="per-step", choices=["per-step", "per-frame"],
+                    help="e2e leg: copy the Gaussian set host->device once per step (the frames of a step share it, as in "
+                         "the device-resident leg; result = losses + the step's summed gradients) or once per frame "
+                         "(every rasteriser call gets fresh host inputs and returns its own gradients)")
+    ap.add_argument("--trace-e2e", default=None, help="write a chrome trace (CUPTI via torch.profiler) of one e2e step here")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU budget of the cpu_baseline leg")
     return ap.parse_args()
 
@@ -410,7 +415,7 @@ def run_b200(args):
             keep_alive.append((lv, img, m2, outs))
             return outs
 
-        def e2e_body():
+        def e2e_body_per_frame():
             cur = torch.cuda.current_stream(dev)
             if lane_s:
                 for ls in lane_s:
@@ -436,6 +441,81 @@ def run_b200(args):
             if lane_s:
                 for ls in lane_s:
                     cur.wait_stream(ls)
+
+        def e2e_body_per_step():
+            """One training step as ExAvatar runs it (train.py:35-57): the frames of the batch render the SAME parameter
+            set, the loss gradients of all frames are summed into the parameters' .grad, the optimiser would read those.
+            Host -> device: the parameter set once, one target image per frame.  Device -> host: the summed gradients
+            and the per-frame losses."""
+            cur = torch.cuda.current_stream(dev)
+            streams = lane_s if lane_s else [cur]
+            for st_ in (lane_s or []):
+                st_.wait_stream(cur)
+            d2h_s.wait_stream(cur)
+            h2d_s.wait_stream(cur)
+            with torch.cuda.stream(h2d_s):
+                params = {k: v.to(dev, non_blocking=True) for k, v in host_assets.items()}
+                ev_p = torch.cuda.Event()
+                ev_p.record(h2d_s)
+                tgts, ev_t = [], []
+                for f in range(F):
+                    tgts.append(host_targets[f].to(dev, non_blocking=True))
+                    e = torch.cuda.Event()
+                    e.record(h2d_s)
+                    ev_t.append(e)
+            keep_alive.append((params, tgts))
+            leaves = []
+            for st_ in streams:  # lane-private leaf views of the one uploaded parameter set
+                st_.wait_event(ev_p)
+                with torch.cuda.stream(st_):
+                    leaves.append({k: v.detach().requires_grad_(wl.backward) for k, v in params.items()})
+            losses = []
+            for f in range(F):
+                fs = streams[f % len(streams)]
+                lv = leaves[f % len(streams)]
+                fs.wait_event(ev_t[f])
+                with torch.cuda.stream(fs):
+                    if use_sh:
+                        img, _, m2 = public_frame(f, leaves=lv)
+                    else:
+                        o = renderer(lv, (H, Wd), cams[f], bg, raster_settings=settings[f])
+                        img, m2 = o["img"], o["mean_2d"]
+                    if wl.backward:
+                        loss = (img - tgts[f]).abs().mean()
+                        loss.backward()  # accumulates into this lane's leaves
+                        losses.append(loss.detach().reshape(1))
+                        keep_alive.append((img, m2, loss))
+                    else:
+                        done = torch.cuda.Event()
+                        done.record(fs)
+                        keep_alive.append((img, m2))
+                        with torch.cuda.stream(d2h_s):
+                            d2h_s.wait_event(done)
+                            host_img.copy_(img.detach(), non_blocking=True)
+            for st_ in (lane_s or []):
+                cur.wait_stream(st_)
+            if wl.backward:
+                total = {k: leaves[0][k].grad for k in host_grads}
+                for lv in leaves[1:]:
+                    if lv[next(iter(host_grads))].grad is not None:
+                        total = {k: total[k] + lv[k].grad for k in host_grads}
+                lvec = torch.cat(losses)
+                keep_alive.append((leaves, total, lvec))
+                done = torch.cuda.Event()
+                done.record(cur)
+                with torch.cuda.stream(d2h_s):
+                    d2h_s.wait_event(done)
+                    host_loss.copy_(lvec, non_blocking=True)
+                    for k in host_grads:
+                        host_grads[k].copy_(total[k], non_blocking=True)
+            cur.wait_stream(d2h_s)
+            cur.wait_stream(h2d_s)
+
+        per_step = args.e2e_upload == "per-step"
+        e2e_body = e2e_body_per_step if per_step else e2e_body_per_frame
+        if per_step:
+            h2d = sum(v.numel() * 4 for v in host_assets.values()) + F * 3 * N * 4
+            d2h = (sum(v.numel() * 4 for v in host_grads.values()) + F * 4) if wl.backward else F * 3 * N * 4
 
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -471,10 +551,19 @@ def run_b200(args):
             e2e_step()
         ke = max(3, min(K, 20))
         ms_e, _, _ = timed(e2e_step, ke)
+        if args.trace_e2e and rank == 0:  # after the timed region: one more step under the profiler
+            from torch.profiler import ProfilerActivity, profile
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                e2e_step()
+                torch.cuda.synchronize(dev)
+            prof.export_chrome_trace(args.trace_e2e)
         if RZ.overflowed():
             raise SystemExit("bench.py: e2e leg overflowed its fixed duplicate capacity; results invalid")
         RZ.set_fixed_capacity(None)
         e2e = {"value": world * F * ke / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+               "upload": args.e2e_upload + (": parameter set once per step + one target image per frame up; summed "
+                                            "gradients + per-frame losses down" if per_step else
+                                            ": every frame uploads the full Gaussian set + target and downloads its gradients"),
                "api": "GaussianRenderer.forward -> GaussianRasterizer (autograd) + L1 loss + backward, pinned host buffers; "
                       + ("whole step captured in a CUDA graph, copies on forked streams" if e2e_graph is not None
                          else "eager, copies on side streams"),

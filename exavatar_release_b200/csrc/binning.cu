@@ -8,6 +8,8 @@
 // Order contract (App. A.2): ascending view depth, ties by ascending Gaussian index.  The 64-bit sort key
 // (depth_bits << 32 | id) gives exactly that for positive floats and makes the result independent of the order in
 // which the scatter's atomics landed, i.e. the pipeline is deterministic.
+#include <cstdlib>
+
 #include "common.cuh"
 
 namespace b2r {
@@ -374,9 +376,9 @@ int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t 
     // faster, 8160 tiles 2x slower than direct atomics)
     if (cx.tiles <= 2048) {
       cudaFuncSetAttribute(scatter_agg_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 96 * 1024);
-      scatter_agg_kernel<<<(sc.P + 255) / 256, 256, smem, st>>>(sc, cx);
+      launch_k(scatter_agg_kernel, (sc.P + 255) / 256, 256, smem, st, true, sc, cx);
     } else {
-      scatter_kernel<<<(sc.P + 255) / 256, 256, 0, st>>>(sc, cx);
+      launch_k(scatter_kernel, (sc.P + 255) / 256, 256, 0, st, true, sc, cx);
     }
   }
   static int sms = 0;
@@ -394,11 +396,11 @@ int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t 
   cudaFuncSetAttribute(sort_tiles_kernel<SORT_LARGE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)large_bytes);
   {
     ProfScope p(K_SORT_SMALL, st);
-    sort_tiles_kernel<SORT_SMALL, ST><<<cx.tiles, ST, small_bytes, st>>>(cx, 0, SORT_SMALL);
+    launch_k(sort_tiles_kernel<SORT_SMALL, ST>, cx.tiles, ST, small_bytes, st, true, cx, 0, SORT_SMALL);
   }
   {
     ProfScope p(K_SORT_LARGE, st);
-    sort_tiles_kernel<SORT_LARGE, 512><<<cx.tiles < sms ? cx.tiles : sms, 512, large_bytes, st>>>(cx, SORT_SMALL, 0x7fffffff);
+    launch_k(sort_tiles_kernel<SORT_LARGE, 512>, cx.tiles < sms ? cx.tiles : sms, 512, large_bytes, st, true, cx, SORT_SMALL, 0x7fffffff);
   }
   return check_launch();
 }

@@ -227,6 +227,52 @@ struct ProfScope {
   ~ProfScope();
 };
 
+// Optional per-CTA timeline (compile with -DB2R_CTA_TRACE; tools/cta_trace.py): every composite CTA records
+// {start ns, end ns, smid, list length} so the schedule (tail, per-SM balance, longest chain) can be reconstructed.
+#ifdef B2R_CTA_TRACE
+static __device__ unsigned long long* g_cta_trace;  // one copy per translation unit, set by b2r_debug_trace_*()
+__device__ __forceinline__ unsigned long long trace_now() {
+  unsigned long long t;
+  asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+  return t;
+}
+__device__ __forceinline__ void trace_end(unsigned long long t0, int n) {
+  if (threadIdx.x == 0 && g_cta_trace) {
+    unsigned smid;
+    asm volatile("mov.u32 %0, %smid;" : "=r"(smid));
+    unsigned long long* d = g_cta_trace + 4ull * blockIdx.x;
+    d[0] = t0; d[1] = trace_now(); d[2] = smid; d[3] = (unsigned long long)n;
+  }
+}
+#define B2R_TRACE_BEGIN() const unsigned long long trace_t0 = trace_now()
+#define B2R_TRACE_END(n) trace_end(trace_t0, (n))
+#else
+#define B2R_TRACE_BEGIN()
+#define B2R_TRACE_END(n)
+#endif
+
+// Kernel launch with an execution priority (a launch attribute; captured into CUDA-graph kernel nodes as well).
+// When several frames are in flight on different streams (plan.py FrameLanes) the block scheduler hands freed SM
+// resources to pending CTAs in launch order, so a 1-CTA scan or a few-hundred-CTA projection of frame B used to wait
+// behind the thousands of composite CTAs frame A still had queued (tools/lanes_timeline.py: 50-120 us gaps).  The
+// short, latency-bound kernels of the chain therefore run at high priority and the two composites at the default.
+int launch_priority(bool high);
+template <typename... KArgs, typename... Args>
+inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool high,
+                     Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributePriority;
+  attr[0].val.priority = launch_priority(high);
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 extern int g_last_cuda_error;
 inline int check_launch() {
   cudaError_t e = cudaGetLastError();

@@ -251,9 +251,9 @@ int launch_composite_bwd2(const B2RScene& sc, const Ctx& cx, const B2RBackwardAr
   cudaMemsetAsync(gacc, 0, (size_t)(sc.P > 0 ? sc.P : 1) * 12 * sizeof(float), st);
   ProfScope p(K_COMPOSITE_BWD, st);
   if (a.dL_ddepth || a.dL_dalpha)
-    composite_bwd2_kernel<true><<<cx.tiles * 4, B2_THREADS, 0, st>>>(sc, cx, a, gacc);
+    launch_k(composite_bwd2_kernel<true>, cx.tiles * 4, B2_THREADS, 0, st, false, sc, cx, a, gacc);
   else
-    composite_bwd2_kernel<false><<<cx.tiles * 4, B2_THREADS, 0, st>>>(sc, cx, a, gacc);
+    launch_k(composite_bwd2_kernel<false>, cx.tiles * 4, B2_THREADS, 0, st, false, sc, cx, a, gacc);
   return check_launch();
 }
 

@@ -31,11 +31,12 @@ struct B3Stage {
   float4 b[B3_BATCH];  // C2, opacity, depth, thr2
   float4 c[B3_BATCH];  // r, g, b, id | clamp bits << 29
 };
-struct B3Compact {     // survivors of one 32-entry chunk, back-to-front; slot 32 = room for the odd-count pad
-  float4 a[33];
-  float4 b[33];        // .w = list position (int bits) instead of thr2
-  float4 c[33];
+constexpr int B3_GROUP = 4;   // splats replayed per trip of the hit loop (their evaluations overlap: ILP 4)
+constexpr int B3_CQ = 36;     // survivor queue: <= 3 left over + 32 new per chunk (+ pad)
+struct B3Compact {            // warp-private queue of cull survivors, back to front
+  float4 r[3][B3_CQ];         // [0] px,py,A2,B2  [1] C2,opacity,depth,list position (int bits)  [2] r,g,b,id bits
 };
+static_assert(B3_QUEUE % B3_GROUP == 0, "phase B runs when whole groups fill the transposition queue");
 
 __device__ __forceinline__ float rcp_approx(float x) {
   float y;
@@ -53,6 +54,7 @@ __global__ void __launch_bounds__(B3_THREADS) composite_bwd3_kernel(const B2RSce
   __shared__ float4 qm1[2][B3_QUEUE];     // C2, opacity, id bits, -
   __shared__ float4 gpix[2][32];          // per pixel of the warp: g_r, g_g, g_b, g_depth
   __shared__ int warp_max_s[2];
+  B2R_TRACE_BEGIN();
 
   const int tile = (int)cx.tile_order[blockIdx.x >> 2];
   const int quad = blockIdx.x & 3;
@@ -89,7 +91,10 @@ __global__ void __launch_bounds__(B3_THREADS) composite_bwd3_kernel(const B2RSce
   if (lane == 0) warp_max_s[warp] = warp_n;
   __syncthreads();
   const int nmax = max(warp_max_s[0], warp_max_s[1]);
-  if (nmax == 0) return;
+  if (nmax == 0) {
+    B2R_TRACE_END(0);
+    return;
+  }
   const int nb = (nmax + B3_BATCH - 1) / B3_BATCH;
 
   // blend state, walked back to front: T, and the scalar form of the "accumulated colour behind me" recurrence
@@ -110,24 +115,37 @@ __global__ void __launch_bounds__(B3_THREADS) composite_bwd3_kernel(const B2RSce
     if (live) {
       m0 = qm0[warp][h];
       m1 = qm1[warp][h];
+      // Two pixel rows of eight per lane.  Within a row dy is constant, so only q, q dx and q dx^2 are summed per
+      // pixel; the dy moments are formed once per row from the row sums.
       const float mx = m0.x - rx0, my = m0.y - ry0;
+      float dxs[8];
 #pragma unroll
-      for (int k = 0; k < PIX; k++) {
-        const int p = half * PIX + k;
-        const float2 t = tb[warp][h][p];
-        const float4 g = gpix[warp][p];
-        const float dx = mx - (float)(p & 7), dy = my - (float)(p >> 3);
-        const float hx = t.x * dx, hy = t.x * dy;
-        Sx += hx;
+      for (int c = 0; c < 8; c++) dxs[c] = mx - (float)c;
+#pragma unroll
+      for (int r = 0; r < 2; r++) {
+        const float dy = my - (float)(half * 2 + r);
+        float Rq = 0.f, Rx = 0.f, Rxx = 0.f;
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+          const int p = half * PIX + r * 8 + c;
+          const float2 t = tb[warp][h][p];
+          const float4 g = gpix[warp][p];
+          const float hx = t.x * dxs[c];
+          Rq += t.x;
+          Rx += hx;
+          Rxx = fmaf(hx, dxs[c], Rxx);
+          Sr = fmaf(t.y, g.x, Sr);
+          Sg = fmaf(t.y, g.y, Sg);
+          Sb = fmaf(t.y, g.z, Sb);
+          if (HAS_DA) Sd = fmaf(t.y, g.w, Sd);
+        }
+        const float hy = Rq * dy;
+        Sq += Rq;
+        Sx += Rx;
+        Sxx += Rxx;
         Sy += hy;
-        Sxx = fmaf(hx, dx, Sxx);
-        Sxy = fmaf(hx, dy, Sxy);
         Syy = fmaf(hy, dy, Syy);
-        Sq += t.x;
-        Sr = fmaf(t.y, g.x, Sr);
-        Sg = fmaf(t.y, g.y, Sg);
-        Sb = fmaf(t.y, g.z, Sb);
-        if (HAS_DA) Sd = fmaf(t.y, g.w, Sd);
+        Sxy = fmaf(Rx, dy, Sxy);
       }
     }
     Sx += __shfl_xor_sync(0xffffffffu, Sx, 16);
@@ -163,30 +181,47 @@ __global__ void __launch_bounds__(B3_THREADS) composite_bwd3_kernel(const B2RSce
     cp_async_commit();
   };
 
-  // one replayed splat: a, bb (bb.w = list position), col are warp-uniform; everything else is per pixel
-  auto replay = [&](const float4 a, const float4 bb, const float4 col, const float p2, const float araw,
-                    const bool valid) {
-    const float ae = valid ? fminf(K_ALPHA_MAX, araw) : 0.f;  // a skipped splat enters with alpha = 0 (identity)
-    const float om = 1.f - ae;
-    const float rcp = rcp_approx(om);
-    const float Tn = T * rcp;
-    float v = fmaf(col.z, g_b, fmaf(col.y, g_g, col.x * g_r));
-    if (HAS_DA) v += fmaf(bb.z, g_d, g_a);
-    B = fmaf(la, lv, olm * B);
-    const float dLda = fmaf(v - B, Tn, -Tfb * rcp);
-    la = ae; olm = om; lv = v; T = Tn;
-    (void)p2;
-    tb[warp][qpos][lane] = make_float2(valid ? araw * dLda : 0.f, ae * Tn);  // q = dL/dG * G (clamp ignored), w
-    if (lane0) {
-      qm0[warp][qpos] = a;
-      qm1[warp][qpos] = make_float4(bb.x, bb.y, col.w, 0.f);
+  // One trip = B3_GROUP queued survivors.  Stage 1 (independent per splat, so the four overlap): exponent, alpha,
+  // validity, the scalar "colour" v = c . g, and the per-splat record for phase B (written by lane 0).  Stage 2: the
+  // short serial recurrences (T, B) and the two numbers per pixel that go to the transposition queue.  No branches
+  // inside a trip; a splat no pixel of the warp accepts still takes a queue slot (all-zero column).
+  auto replay_group = [&](const int k) {
+    float araw[B3_GROUP], vv[B3_GROUP];
+    bool valid[B3_GROUP];
+#pragma unroll
+    for (int u = 0; u < B3_GROUP; u++) {
+      const float4 a = cw.r[0][k + u], bb = cw.r[1][k + u], col = cw.r[2][k + u];
+      const float dx = a.x - pxf, dy = a.y - pyf;
+      const float p2 = a.z * dx * dx + bb.x * dy * dy + a.w * dx * dy;
+      araw[u] = bb.y * ex2_approx(p2);
+      valid[u] = (__float_as_int(bb.w) < my_n) && (p2 <= 0.f) && (araw[u] >= K_ALPHA_MIN);
+      float v = fmaf(col.z, g_b, fmaf(col.y, g_g, col.x * g_r));
+      if (HAS_DA) v += fmaf(bb.z, g_d, g_a);
+      vv[u] = v;
+      if (lane0) {
+        qm0[warp][qpos + u] = a;
+        qm1[warp][qpos + u] = make_float4(bb.x, bb.y, col.w, 0.f);
+      }
     }
-    if (++qpos == B3_QUEUE) {
+#pragma unroll
+    for (int u = 0; u < B3_GROUP; u++) {
+      const float ae = valid[u] ? fminf(K_ALPHA_MAX, araw[u]) : 0.f;  // a skipped splat enters with alpha = 0 (identity)
+      const float om = 1.f - ae;
+      const float rcp = rcp_approx(om);
+      const float Tn = T * rcp;
+      B = fmaf(la, lv, olm * B);
+      const float dLda = fmaf(vv[u] - B, Tn, -Tfb * rcp);
+      la = ae; olm = om; lv = vv[u]; T = Tn;
+      tb[warp][qpos + u][lane] = make_float2(valid[u] ? araw[u] * dLda : 0.f, ae * Tn);  // q = dL/dG * G (clamp ignored), w
+    }
+    qpos += B3_GROUP;
+    if (qpos == B3_QUEUE) {
       drain(B3_QUEUE);
       qpos = 0;
     }
   };
 
+  int fill = 0;  // warp-uniform: survivors waiting in the queue (< B3_GROUP between chunks)
   issue(nb - 1);
   for (int b = nb - 1; b >= 0; b--) {
     cp_async_wait<0>();
@@ -207,38 +242,39 @@ __global__ void __launch_bounds__(B3_THREADS) composite_bwd3_kernel(const B2RSce
       }
       const unsigned mask = __ballot_sync(0xffffffffu, hit);
       if (mask == 0u) continue;
-      const int n = __popc(mask);
-      if (hit) {  // back to front: the highest surviving list position goes to slot 0
-        const int slot = __popc(mask & lanes_above);
-        cw.a[slot] = a;
-        cw.b[slot] = make_float4(bb.x, bb.y, bb.z, __int_as_float(pos));
-        cw.c[slot] = s.c[idx];
+      if (hit) {  // back to front: the highest surviving list position is queued first
+        const int slot = fill + __popc(mask & lanes_above);
+        cw.r[0][slot] = a;
+        cw.r[1][slot] = make_float4(bb.x, bb.y, bb.z, __int_as_float(pos));
+        cw.r[2][slot] = s.c[idx];
       }
-      if (lane0 && (n & 1)) {  // pad to an even count with a splat that can never be valid
-        cw.a[n] = make_float4(0.f, 0.f, 0.f, 0.f);
-        cw.b[n] = make_float4(0.f, 0.f, 0.f, __int_as_float(0x7fffffff));
-        cw.c[n] = make_float4(0.f, 0.f, 0.f, 0.f);
-      }
+      fill += __popc(mask);
       __syncwarp();
-      // Two survivors per trip: their exponent evaluations (shared loads, MUFU) are independent and overlap; only the
-      // short blend-state recurrence is serial.
-      for (int k = 0; k < n; k += 2) {
-        const float4 a0 = cw.a[k], b0 = cw.b[k], col0 = cw.c[k];
-        const float4 a1 = cw.a[k + 1], b1 = cw.b[k + 1], col1 = cw.c[k + 1];
-        const float dx0 = a0.x - pxf, dy0 = a0.y - pyf, dx1 = a1.x - pxf, dy1 = a1.y - pyf;
-        const float p20 = a0.z * dx0 * dx0 + b0.x * dy0 * dy0 + a0.w * dx0 * dy0;
-        const float p21 = a1.z * dx1 * dx1 + b1.x * dy1 * dy1 + a1.w * dx1 * dy1;
-        const float ar0 = b0.y * ex2_approx(p20), ar1 = b1.y * ex2_approx(p21);
-        const bool v0 = (__float_as_int(b0.w) < my_n) && (p20 <= 0.f) && (ar0 >= K_ALPHA_MIN);
-        const bool v1 = (__float_as_int(b1.w) < my_n) && (p21 <= 0.f) && (ar1 >= K_ALPHA_MIN);
-        if (__any_sync(0xffffffffu, v0)) replay(a0, b0, col0, p20, ar0, v0);
-        if (__any_sync(0xffffffffu, v1)) replay(a1, b1, col1, p21, ar1, v1);
+      int k = 0;
+      for (; k + B3_GROUP <= fill; k += B3_GROUP) replay_group(k);
+      const int left = fill - k;
+      __syncwarp();
+      if (k > 0 && lane < 3 * left) {  // move the <= 3 leftover records to the front (sources are slots >= 4)
+        const int t = (lane >= left) + (lane >= 2 * left), j = lane - t * left;
+        cw.r[t][j] = cw.r[t][k + j];
       }
-      __syncwarp();  // the compact buffer is rewritten by the next chunk
+      fill = left;
+      __syncwarp();  // queue reads / moves before the next append
     }
+  }
+  if (fill > 0) {  // flush: pad the last group with splats that can never be valid (list position INT_MAX); their
+                   // opacity is 1 because phase B divides by it
+    if (lane >= fill && lane < B3_GROUP) {
+      cw.r[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cw.r[1][lane] = make_float4(0.f, 1.f, 0.f, __int_as_float(0x7fffffff));
+      cw.r[2][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    replay_group(0);
   }
   if (qpos > 0) drain(qpos);
   if (threadIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&cx.status->consumed_bwd), (unsigned long long)nmax);
+  B2R_TRACE_END(nmax);
 }
 
 int launch_composite_bwd2(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, float* gacc, cudaStream_t st);
@@ -250,10 +286,16 @@ int launch_composite_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArg
   cudaMemsetAsync(gacc, 0, (size_t)(sc.P > 0 ? sc.P : 1) * 12 * sizeof(float), st);
   ProfScope p(K_COMPOSITE_BWD, st);
   if (a.dL_ddepth || a.dL_dalpha)
-    composite_bwd3_kernel<true><<<cx.tiles * 4, B3_THREADS, 0, st>>>(sc, cx, a, gacc);
+    launch_k(composite_bwd3_kernel<true>, cx.tiles * 4, B3_THREADS, 0, st, false, sc, cx, a, gacc);
   else
-    composite_bwd3_kernel<false><<<cx.tiles * 4, B3_THREADS, 0, st>>>(sc, cx, a, gacc);
+    launch_k(composite_bwd3_kernel<false>, cx.tiles * 4, B3_THREADS, 0, st, false, sc, cx, a, gacc);
   return check_launch();
 }
 
 }  // namespace b2r
+
+#ifdef B2R_CTA_TRACE
+extern "C" int b2r_debug_trace_bwd(unsigned long long* buf) {
+  return (int)cudaMemcpyToSymbol(b2r::g_cta_trace, &buf, sizeof(buf));
+}
+#endif

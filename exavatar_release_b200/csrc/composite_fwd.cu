@@ -28,7 +28,12 @@ constexpr int FWD_PER_THREAD = FWD_BATCH / FWD_THREADS;
 struct FwdStage {
   float4 a[FWD_BATCH];  // px, py, A2, B2
   float4 b[FWD_BATCH];  // C2, opacity, depth, thr2
-  float4 c[FWD_BATCH];  // r, g, b, bits
+  float4 c[FWD_BATCH];  // r, g, b, id bits
+};
+constexpr int FWD_GROUP = 4;   // splats blended per trip of the hit loop (their evaluations overlap: ILP 4)
+constexpr int FWD_CQ = 36;     // survivor queue: <= 3 left over + 32 new per chunk (+ pad)
+struct FwdCompact {            // warp-private queue of cull survivors in list order
+  float4 r[3][FWD_CQ];         // [0] px,py,A2,B2  [1] C2,opacity,depth,1-based list position (int bits)  [2] r,g,b,-
 };
 
 __device__ __forceinline__ void store4(float* base, bool vec_ok, int lane, float v, bool inside) {
@@ -45,6 +50,8 @@ __device__ __forceinline__ void store4(float* base, bool vec_ok, int lane, float
 __global__ void __launch_bounds__(FWD_THREADS) composite_fwd_kernel(const B2RScene sc, const Ctx cx,
                                                                     const B2RForwardOutputs out, const int vec_ok) {
   __shared__ FwdStage stage[2];
+  __shared__ FwdCompact compact[2];
+  B2R_TRACE_BEGIN();
   const int tile = (int)cx.tile_order[blockIdx.x >> 2];
   const int quad = blockIdx.x & 3;
   const int tx = tile % cx.gx, ty = tile / cx.gx;
@@ -63,9 +70,14 @@ __global__ void __launch_bounds__(FWD_THREADS) composite_fwd_kernel(const B2RSce
   const uint32_t* ids = cx.dup_ids + range.x;
   const int nb = (n + FWD_BATCH - 1) / FWD_BATCH;
 
-  float T = 1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Dp = 0.f, Aa = 0.f;
+  // Blend state.  A finished pixel (T(1-a) < 1e-4 reached, or outside the image) is marked by the SIGN of T: the
+  // magnitude is still the transmittance that goes to final_T, and "alive" is one compare folded into the chain of
+  // predicate tests below -- no separate flag register to maintain.
+  float T = inside ? 1.f : -1.f, Cr = 0.f, Cg = 0.f, Cb = 0.f, Dp = 0.f, Aa = 0.f;
   uint32_t last = 0;
-  bool done = !inside;
+  FwdCompact& cw = compact[warp];
+  const unsigned lanes_below = (1u << lane) - 1u;
+  int fill = 0;  // warp-uniform: survivors waiting in the queue (< FWD_GROUP between chunks)
 
   auto issue = [&](int b) {
     FwdStage& s = stage[b & 1];
@@ -84,84 +96,106 @@ __global__ void __launch_bounds__(FWD_THREADS) composite_fwd_kernel(const B2RSce
     cp_async_commit();
   };
 
+  // One trip = FWD_GROUP queued splats.  Their exponent evaluations are independent of the blend state and of each
+  // other, so they overlap (shared loads, FMA chain, MUFU); only the short T recurrence that follows is serial.
+  // Branch-free (App. A.3): a splat is skipped unless the pixel is alive, power <= 0 and alpha >= 1/255; a splat that
+  // would drop T(1-a) below 1e-4 finishes the pixel WITHOUT being applied.
+  auto blend_group = [&](const int k) {
+    float al[FWD_GROUP];
+    bool ok[FWD_GROUP];
+    float4 col[FWD_GROUP];
+    float dep[FWD_GROUP];
+    uint32_t pos[FWD_GROUP];
+#pragma unroll
+    for (int u = 0; u < FWD_GROUP; u++) {
+      const float4 a = cw.r[0][k + u], bb = cw.r[1][k + u];
+      col[u] = cw.r[2][k + u];
+      const float dx = a.x - pxf, dy = a.y - pyf;
+      const float p2 = a.z * dx * dx + bb.x * dy * dy + a.w * dx * dy;
+      const float ar = bb.y * ex2_approx(p2);
+      al[u] = fminf(K_ALPHA_MAX, ar);
+      ok[u] = (ar >= K_ALPHA_MIN) & (p2 <= 0.f);
+      dep[u] = bb.z;
+      pos[u] = (uint32_t)__float_as_int(bb.w);
+    }
+#pragma unroll
+    for (int u = 0; u < FWD_GROUP; u++) {
+      const bool v = ok[u] & (T > 0.f);
+      const float test = T * (1.f - al[u]);
+      const float w = al[u] * T;
+      const bool stop = v & (test < K_T_MIN);
+      const bool use = v & !stop;
+      Cr = use ? fmaf(col[u].x, w, Cr) : Cr;  // predicated accumulates: a skipped splat must not touch the sums at all
+      Cg = use ? fmaf(col[u].y, w, Cg) : Cg;
+      Cb = use ? fmaf(col[u].z, w, Cb) : Cb;
+      Dp = use ? fmaf(dep[u], w, Dp) : Dp;
+      Aa = use ? Aa + w : Aa;
+      last = use ? pos[u] : last;
+      T = use ? test : (stop ? -T : T);
+    }
+  };
+
   int staged = 0;
   if (nb > 0) issue(0);
   for (int b = 0; b < nb; b++) {
     cp_async_wait<0>();
-    if (__syncthreads_and(done)) break;  // batch b visible; everyone is past batch b-1
+    if (__syncthreads_and(!(T > 0.f))) break;  // batch b visible; everyone is past batch b-1
     if (b + 1 < nb) issue(b + 1);
     const int count = min(FWD_BATCH, n - b * FWD_BATCH);
     staged += count;
     const FwdStage& s = stage[b & 1];
-    bool warp_live = __any_sync(0xffffffffu, !done);
+    bool warp_live = __any_sync(0xffffffffu, T > 0.f);
     for (int c0 = 0; c0 < count && warp_live; c0 += 32) {
       const int idx = c0 + lane;
       bool hit = false;
+      float4 a, bb;
       if (idx < count) {
-        const float4 a = s.a[idx];
-        const float4 bb = s.b[idx];
+        a = s.a[idx];
+        bb = s.b[idx];
         hit = !(region_max_p2(a.x, a.y, a.z, a.w, bb.x, rx0, ry0, rx1, ry1) < bb.w);
       }
-      unsigned mask = __ballot_sync(0xffffffffu, hit);
-      // Walk the surviving splats two at a time: the two exponent evaluations are independent (ILP 2); only the
-      // transmittance recurrence is serial, and it is applied branch-free (selects), so the only branches in this
-      // loop are warp-uniform.
-      while (mask) {
-        const int k0 = __ffs(mask) - 1;
-        mask &= mask - 1;
-        const bool two = mask != 0;
-        const int k1 = two ? __ffs(mask) - 1 : k0;
-        mask &= mask - 1;  // no-op when mask == 0
-        const int j0 = c0 + k0, j1 = c0 + k1;
-        const float4 a0 = s.a[j0], b0 = s.b[j0], col0 = s.c[j0];
-        const float4 a1 = s.a[j1], b1 = s.b[j1], col1 = s.c[j1];
-        const float dx0 = a0.x - pxf, dy0 = a0.y - pyf;
-        const float dx1 = a1.x - pxf, dy1 = a1.y - pyf;
-        const float p20 = a0.z * dx0 * dx0 + b0.x * dy0 * dy0 + a0.w * dx0 * dy0;
-        const float p21 = a1.z * dx1 * dx1 + b1.x * dy1 * dy1 + a1.w * dx1 * dy1;
-        const float al0 = fminf(K_ALPHA_MAX, b0.y * ex2_approx(p20));
-        const float al1 = fminf(K_ALPHA_MAX, b1.y * ex2_approx(p21));
-        const bool ok0 = (p20 <= 0.f) & (al0 >= K_ALPHA_MIN);
-        const bool ok1 = two & (p21 <= 0.f) & (al1 >= K_ALPHA_MIN);
-        {
-          const bool v = ok0 & !done;
-          const float test = T * (1.f - al0);
-          const bool stop = v & (test < K_T_MIN);  // this splat is not applied (App. A.3)
-          done |= stop;
-          const bool use = v & !stop;
-          const float w = al0 * T;  // predicated accumulates: a skipped splat must not touch the sums at all
-          Cr = use ? fmaf(col0.x, w, Cr) : Cr;
-          Cg = use ? fmaf(col0.y, w, Cg) : Cg;
-          Cb = use ? fmaf(col0.z, w, Cb) : Cb;
-          Dp = use ? fmaf(b0.z, w, Dp) : Dp;
-          Aa = use ? Aa + w : Aa;
-          T = use ? test : T;
-          last = use ? (uint32_t)(b * FWD_BATCH + j0 + 1) : last;
-        }
-        {
-          const bool v = ok1 & !done;
-          const float test = T * (1.f - al1);
-          const bool stop = v & (test < K_T_MIN);
-          done |= stop;
-          const bool use = v & !stop;
-          const float w = al1 * T;  // predicated accumulates: a skipped splat must not touch the sums at all
-          Cr = use ? fmaf(col1.x, w, Cr) : Cr;
-          Cg = use ? fmaf(col1.y, w, Cg) : Cg;
-          Cb = use ? fmaf(col1.z, w, Cb) : Cb;
-          Dp = use ? fmaf(b1.z, w, Dp) : Dp;
-          Aa = use ? Aa + w : Aa;
-          T = use ? test : T;
-          last = use ? (uint32_t)(b * FWD_BATCH + j1 + 1) : last;
+      const unsigned mask = __ballot_sync(0xffffffffu, hit);
+      if (mask == 0u) continue;
+      // Append the survivors (list order) to the warp's queue: the hit loop then walks consecutive slots, FWD_GROUP at
+      // a time, instead of find-first-set + index arithmetic per splat; what does not fill a group waits for the
+      // next chunk.
+      if (hit) {
+        const int slot = fill + __popc(mask & lanes_below);
+        cw.r[0][slot] = a;
+        cw.r[1][slot] = make_float4(bb.x, bb.y, bb.z, __int_as_float(b * FWD_BATCH + idx + 1));
+        cw.r[2][slot] = s.c[idx];
+      }
+      fill += __popc(mask);
+      __syncwarp();
+      int k = 0;
+      for (; k + FWD_GROUP <= fill; k += FWD_GROUP) blend_group(k);
+      const int left = fill - k;
+      if (k > 0) {  // move the <= 3 leftover records to the front (sources are slots >= 4: no overlap)
+        __syncwarp();
+        if (lane < 3 * left) {
+          const int t = (lane >= left) + (lane >= 2 * left), j = lane - t * left;
+          cw.r[t][j] = cw.r[t][k + j];
         }
       }
-      warp_live = __any_sync(0xffffffffu, !done);
+      fill = left;
+      warp_live = __any_sync(0xffffffffu, T > 0.f);  // also orders the queue reads / moves before the next append
     }
+  }
+  if (fill > 0) {  // flush: pad the last group with splats of opacity 0 (alpha 0 < 1/255 => skipped)
+    if (lane >= fill && lane < FWD_GROUP) {
+      cw.r[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cw.r[1][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cw.r[2][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    __syncwarp();
+    blend_group(0);
   }
   cp_async_wait<0>();
 
   // consumed_fwd counts list entries per TILE: four quarter-CTAs each add a quarter of what they staged
   if (threadIdx.x == 0 && staged) atomicAdd(reinterpret_cast<unsigned long long*>(&cx.status->consumed_fwd), (unsigned long long)staged);
 
+  T = fabsf(T);
   const size_t N = (size_t)W * H;
   const size_t pix = (size_t)py * W + px;
   const float bg0 = __ldg(sc.bg), bg1 = __ldg(sc.bg + 1), bg2 = __ldg(sc.bg + 2);
@@ -173,6 +207,7 @@ __global__ void __launch_bounds__(FWD_THREADS) composite_fwd_kernel(const B2RSce
   store4(out.alpha + pix, v, lane, Aa, inside);
   store4(cx.final_T + pix, v, lane, T, inside);
   store4(reinterpret_cast<float*>(cx.n_contrib) + pix, v, lane, __uint_as_float(last), inside);
+  B2R_TRACE_END(n);
 }
 
 int launch_composite_fwd(const B2RScene& sc, const Ctx& cx, const B2RForwardOutputs& out, cudaStream_t st) {
@@ -181,9 +216,15 @@ int launch_composite_fwd(const B2RScene& sc, const Ctx& cx, const B2RForwardOutp
                      al16(cx.n_contrib);
   {
     ProfScope p(K_COMPOSITE_FWD, st);
-    composite_fwd_kernel<<<cx.tiles * 4, FWD_THREADS, 0, st>>>(sc, cx, out, vec_ok);
+    launch_k(composite_fwd_kernel, cx.tiles * 4, FWD_THREADS, 0, st, false, sc, cx, out, vec_ok);
   }
   return check_launch();
 }
 
 }  // namespace b2r
+
+#ifdef B2R_CTA_TRACE
+extern "C" int b2r_debug_trace_fwd(unsigned long long* buf) {
+  return (int)cudaMemcpyToSymbol(b2r::g_cta_trace, &buf, sizeof(buf));
+}
+#endif

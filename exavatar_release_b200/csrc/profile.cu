@@ -3,12 +3,24 @@
 // launched on (torch.cuda.Event only sees torch's own ops), and to report how many of OUR kernels ran in the timed
 // region.  Disabled by default: when off, a ProfScope costs one relaxed atomic increment.
 #include <atomic>
+#include <cstdlib>
 #include <mutex>
 #include <vector>
 
 #include "common.cuh"
 
 namespace b2r {
+
+int launch_priority(bool high) {
+  static int least = 0, greatest = 0;
+  static bool init = false;
+  if (!init) {
+    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) least = greatest = 0;
+    if (getenv("B2R_NO_PRIORITY")) greatest = least;  // A/B switch for measurements
+    init = true;
+  }
+  return high ? greatest : least;
+}
 
 static std::atomic<int> g_prof_on{0};
 static std::atomic<unsigned long long> g_launches{0};

@@ -230,13 +230,18 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx) {
   }
 }
 
+// resets the status block and the per-tile counters the projection kernel accumulates into
 __global__ void status_reset_kernel(const Ctx cx) {
-  B2RStatus* s = cx.status;
-  s->num_dups = 0;
-  s->overflow = 0;
-  s->num_visible = 0;
-  s->consumed_fwd = 0;
-  s->consumed_bwd = 0;
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (t < cx.tiles) cx.tile_count[t] = 0u;
+  if (t == 0) {
+    B2RStatus* s = cx.status;
+    s->num_dups = 0;
+    s->overflow = 0;
+    s->num_visible = 0;
+    s->consumed_fwd = 0;
+    s->consumed_bwd = 0;
+  }
 }
 
 __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, const float* __restrict__ view,
@@ -249,26 +254,25 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 }
 
 int launch_project(const B2RScene& sc, const Ctx& cx, int32_t* radii, cudaStream_t st) {
-  cudaMemsetAsync(cx.tile_count, 0, (size_t)cx.tiles * 4, st);
-  { ProfScope p(K_MISC, st); status_reset_kernel<<<1, 1, 0, st>>>(cx); }
+  { ProfScope p(K_MISC, st); launch_k(status_reset_kernel, (cx.tiles + 1023) / 1024, 1024, 0, st, true, cx); }
   if (sc.P > 0) {
     ProfScope p(K_PROJECT, st);
     const size_t smem = (size_t)cx.tiles * 4;
     const int aggregate = cx.tiles <= 2048;  // beyond that the per-CTA sweeps over the tile table cost more than they save
-    project_kernel<<<(sc.P + 255) / 256, 256, aggregate ? smem : 0, st>>>(sc, cx, radii, aggregate);
+    launch_k(project_kernel, (sc.P + 255) / 256, 256, aggregate ? smem : 0, st, true, sc, cx, radii, aggregate);
   }
-  { ProfScope p(K_TILE_SCAN, st); tile_scan_kernel<<<1, 1024, 0, st>>>(cx); }
+  { ProfScope p(K_TILE_SCAN, st); launch_k(tile_scan_kernel, 1, 1024, 0, st, true, cx); }
   return check_launch();
 }
 
 void launch_tile_scan(const Ctx& cx, cudaStream_t st) {
   ProfScope p(K_TILE_SCAN, st);
-  tile_scan_kernel<<<1, 1024, 0, st>>>(cx);
+  launch_k(tile_scan_kernel, 1, 1024, 0, st, true, cx);
 }
 
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t st) {
   ProfScope p(K_MISC, st, P > 0 ? 1 : 0);
-  if (P > 0) mark_visible_kernel<<<(P + 255) / 256, 256, 0, st>>>(P, means3D, view, present);
+  if (P > 0) launch_k(mark_visible_kernel, (P + 255) / 256, 256, 0, st, true, P, means3D, view, present);
   return check_launch();
 }
 

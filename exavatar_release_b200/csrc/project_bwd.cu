@@ -241,7 +241,7 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
 
 int launch_project_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, const float* gacc, cudaStream_t st) {
   ProfScope p(K_PROJECT_BWD, st, sc.P > 0 ? 1 : 0);
-  if (sc.P > 0) project_bwd_kernel<<<(sc.P + 255) / 256, 256, 0, st>>>(sc, cx, a, gacc);
+  if (sc.P > 0) launch_k(project_bwd_kernel, (sc.P + 255) / 256, 256, 0, st, true, sc, cx, a, gacc);
   return check_launch();
 }
 

@@ -284,6 +284,7 @@ class _RasterizeGaussians(torch.autograd.Function):
             if raster_settings.debug:  # reference behaviour with debug=True: dump the arguments, re-raise
                 torch.save(tuple(None if a is None else a.cpu() for a in args), "snapshot_fw.dump")
             raise
+        ctx.set_materialize_grads(False)  # unused outputs (depth, alpha) arrive as None, not as zero images
         ctx.cx = cx
         ctx.has = (sh is not None and sh.numel() > 0, colors_precomp is not None and colors_precomp.numel() > 0,
                    scales is not None and scales.numel() > 0, rotations is not None and rotations.numel() > 0,
@@ -296,6 +297,11 @@ class _RasterizeGaussians(torch.autograd.Function):
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha):
         cx = ctx.cx
         m3s, m2s, ops = ctx.shapes
+        if grad_color is None and grad_depth is None and grad_alpha is None:
+            return (None,) * 9
+        if grad_color is None:  # only depth / alpha were used downstream
+            ref = grad_depth if grad_depth is not None else grad_alpha
+            grad_color = torch.zeros((3,) + tuple(ref.shape[-2:]), dtype=torch.float32, device=ref.device)
         if cx is None:  # P == 0
             z = lambda s: torch.zeros(s, dtype=torch.float32, device=grad_color.device)
             return z(m3s), z(m2s), None, None, z(ops), None, None, None, None

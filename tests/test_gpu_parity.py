@@ -461,6 +461,34 @@ def test_frame_lanes_match_serial_accumulation(dev):
     assert torch.allclose(lanes.bucket, flat, **tol)
 
 
+def test_unused_outputs_get_no_materialised_gradients(dev):
+    """A loss on depth alone (colour / alpha unused) == explicit zero colour gradient; a loss on colour alone takes the
+    kernel variant without depth / alpha gradients (autograd hands the node None for unused outputs)."""
+    rz = RZ()
+    a = {k: v.to(dev) for k, v in make_assets("T1", seed=0).items()}
+    st = workload_settings("T1", yaw=3.0, device=dev, settings_cls=rz.GaussianRasterizationSettings)
+    P = a["mean_3d"].shape[0]
+
+    def run(loss_fn):
+        lv = {k: v.clone().requires_grad_() for k, v in a.items()}
+        m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+        out = rz.GaussianRasterizer(st)(means3D=lv["mean_3d"], means2D=m2, opacities=lv["opacity"],
+                                        colors_precomp=lv["rgb"], scales=lv["scale"], rotations=lv["rotation"])
+        loss_fn(out).backward()
+        return lv, m2
+
+    gd = make_grad_image("T1", 1).to(dev)[:1]
+    lv1, m1 = run(lambda o: (o[2] * gd).sum())
+    lv2, m2_ = run(lambda o: (o[2] * gd).sum() + (o[0] * 0.0).sum() + (o[3] * 0.0).sum())
+    # the two runs differ only in the arrival order of the fp32 vector reductions
+    close = lambda x, y: torch.allclose(x, y, rtol=1e-4, atol=1e-5 * float(y.abs().max()) + 1e-12)
+    for k in lv1:
+        assert close(lv1[k].grad, lv2[k].grad), k
+    assert close(m1.grad, m2_.grad)
+    assert float(lv1["mean_3d"].grad.abs().sum()) > 0
+    assert float(lv1["rgb"].grad.abs().max()) == 0.0
+
+
 def test_renderer_end_to_end_on_gpu(dev):
     from exavatar_release_b200 import GaussianRenderer
     from exavatar_release_b200.camera import look_at_cam_param
