@@ -165,8 +165,7 @@ __device__ __forceinline__ void bitonic_sort(KeyPtr key, const int n, const int 
 // ---------------------------------------------------------------------------------------------------------------
 // K3: per-tile sort.  Order contract (App. A.2): ascending view depth, ties by ascending Gaussian index.
 //
-// One CTA per tile (CTAs stride over cx.tile_order, longest list first).  Lists of <= 128 entries use the bitonic
-// network on 64-bit (depth, id) keys.  Longer lists use an LSD radix sort in shared memory on the 32-bit depth bits
+// One CTA per tile (CTAs stride over cx.tile_order, longest list first).  Lists of <= 32 entries are rank-sorted in registers.  Longer lists use an LSD radix sort in shared memory on the 32-bit depth bits
 // (positive floats order like unsigned integers) carrying a 16-bit local index:
 //   * 8-bit digits; a digit position on which every key of the tile agrees is skipped (the exponent byte almost
 //     always is), so most tiles need 3 passes;
@@ -176,7 +175,20 @@ __device__ __forceinline__ void bitonic_sort(KeyPtr key, const int n, const int 
 //     an odd-even fix-up, which makes the result independent of the scatter's atomic arrival order.
 // Lists longer than CAP (16384) fall back to the in-place bitonic network in global memory.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int SORT_BITONIC_MAX = 128;
+
+// Lanes holding the same 8-bit digit (invalid lanes match nobody).  Eight ballots instead of MATCH.ANY: on sm_100a
+// MATCH.ANY measured an order of magnitude slower than this sequence (tools/cta_trace.py on the sort kernel: a
+// 2000-entry tile took 31 us with it).
+__device__ __forceinline__ unsigned match_digit(const uint32_t d, const bool valid) {
+  unsigned peers = __ballot_sync(0xffffffffu, valid);
+#pragma unroll
+  for (int bit = 0; bit < 8; bit++) {
+    const bool on = (d >> bit) & 1u;
+    const unsigned b = __ballot_sync(0xffffffffu, on);
+    peers &= on ? b : ~b;
+  }
+  return valid ? peers : 0u;
+}
 
 template <int CAP, int THREADS>
 struct RadixSmem {
@@ -227,7 +239,7 @@ __device__ __forceinline__ void radix_sort_tile(const uint2* __restrict__ src, u
       const int i = base + lane;
       const bool valid = i < c_end;
       const uint32_t d = valid ? ((kin[i] >> shift) & 0xffu) : (256u + lane);
-      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const unsigned peers = match_digit(d, valid);
       if (valid && (peers & ((1u << lane) - 1u)) == 0u) myhist[d] = (uint16_t)(myhist[d] + __popc(peers));
       __syncwarp();
     }
@@ -277,7 +289,7 @@ __device__ __forceinline__ void radix_sort_tile(const uint2* __restrict__ src, u
       const bool valid = i < c_end;
       const uint32_t k = valid ? kin[i] : 0u;
       const uint32_t d = valid ? ((k >> shift) & 0xffu) : (256u + lane);
-      const unsigned peers = __match_any_sync(0xffffffffu, d);
+      const unsigned peers = match_digit(d, valid);
       const unsigned below = peers & ((1u << lane) - 1u);
       uint32_t start = 0;
       if (valid && below == 0u) {
@@ -319,30 +331,133 @@ __device__ __forceinline__ void radix_sort_tile(const uint2* __restrict__ src, u
   __syncthreads();  // shared memory is reused by the next tile of this CTA
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-class sort: one WARP per tile for lists shorter than 512 entries (88 % of the tiles of workload C2, median
+// 165 entries).  Same order contract and the same LSD radix scheme as radix_sort_tile, but warp-synchronous: no CTA
+// barriers, 6.6 KB of shared memory per warp, eight tiles per 256-thread CTA.  The CTA-wide version spent most of its
+// time in ~20 barriers per tile with seven of eight warps idle, while holding all 64 warp slots of the SM.
+// ---------------------------------------------------------------------------------------------------------------
+constexpr int WSORT_CAP = 512;
+constexpr size_t WSORT_BYTES = (size_t)WSORT_CAP * 12 + 256 * 2;  // keyA, keyB (u32), idxA, idxB (u16), hist (u16)
+
+__device__ __forceinline__ void warp_sort_tile(const uint2* __restrict__ src, uint32_t* __restrict__ dst, const int n,
+                                               unsigned char* smem_warp) {
+  const int lane = threadIdx.x & 31;
+  const unsigned below_mask = (1u << lane) - 1u;
+  if (n <= 0) return;
+  if (n <= 32) {  // rank sort in registers: position = number of entries with a smaller (depth, id)
+    const uint2 kv = lane < n ? src[lane] : make_uint2(0xffffffffu, 0xffffffffu);
+    const unsigned long long me = ((unsigned long long)kv.x << 32) | kv.y;
+    int rank = 0;
+    for (int j = 0; j < n; j++) {
+      const unsigned long long o = __shfl_sync(0xffffffffu, me, j);
+      rank += (o < me) ? 1 : 0;
+    }
+    if (lane < n) dst[rank] = kv.y;
+    return;
+  }
+  uint32_t* keyA = reinterpret_cast<uint32_t*>(smem_warp);
+  uint32_t* keyB = keyA + WSORT_CAP;
+  uint16_t* idxA = reinterpret_cast<uint16_t*>(keyB + WSORT_CAP);
+  uint16_t* idxB = idxA + WSORT_CAP;
+  uint16_t* hist = idxB + WSORT_CAP;  // [256]
+  uint32_t vor = 0u, vand = 0xffffffffu;
+  for (int i = lane; i < n; i += 32) {
+    const uint32_t k = src[i].x;
+    keyA[i] = k;
+    idxA[i] = (uint16_t)i;
+    vor |= k;
+    vand &= k;
+  }
+  const uint32_t differ = __reduce_or_sync(0xffffffffu, vor) ^ __reduce_and_sync(0xffffffffu, vand);
+  __syncwarp();
+  uint32_t* kin = keyA; uint32_t* kout = keyB;
+  uint16_t* iin = idxA; uint16_t* iout = idxB;
+  for (int pass = 0; pass < 4; pass++) {
+    const int shift = 8 * pass;
+    if (((differ >> shift) & 0xffu) == 0u) continue;  // warp-uniform: the whole tile agrees on this digit
+    reinterpret_cast<uint4*>(hist)[lane] = make_uint4(0u, 0u, 0u, 0u);  // 32 lanes x 16 bytes = 256 x u16
+    __syncwarp();
+    for (int base = 0; base < n; base += 32) {
+      const int i = base + lane;
+      const bool valid = i < n;
+      const uint32_t d = valid ? ((kin[i] >> shift) & 0xffu) : (256u + lane);
+      const unsigned peers = match_digit(d, valid);
+      if (valid && (peers & below_mask) == 0u) hist[d] = (uint16_t)(hist[d] + __popc(peers));
+      __syncwarp();
+    }
+    // exclusive scan of the 256 counters: lane owns digits 8*lane .. 8*lane+7
+    uint32_t c[8], total = 0;
+#pragma unroll
+    for (int r = 0; r < 8; r++) { c[r] = hist[8 * lane + r]; total += c[r]; }
+    uint32_t incl = total;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const uint32_t v = __shfl_up_sync(0xffffffffu, incl, o);
+      if (lane >= o) incl += v;
+    }
+    uint32_t run = incl - total;
+#pragma unroll
+    for (int r = 0; r < 8; r++) { hist[8 * lane + r] = (uint16_t)run; run += c[r]; }
+    __syncwarp();
+    for (int base = 0; base < n; base += 32) {  // stable scatter
+      const int i = base + lane;
+      const bool valid = i < n;
+      const uint32_t k = valid ? kin[i] : 0u;
+      const uint32_t d = valid ? ((k >> shift) & 0xffu) : (256u + lane);
+      const unsigned peers = match_digit(d, valid);
+      const unsigned below = peers & below_mask;
+      uint32_t start = 0;
+      if (valid && below == 0u) {
+        start = hist[d];
+        hist[d] = (uint16_t)(start + __popc(peers));
+      }
+      start = __shfl_sync(0xffffffffu, start, __ffs(peers) - 1);
+      if (valid) {
+        const uint32_t o = start + __popc(below);
+        kout[o] = k;
+        iout[o] = iin[i];
+      }
+      __syncwarp();
+    }
+    { uint32_t* t = kin; kin = kout; kout = t; }
+    { uint16_t* t = iin; iin = iout; iout = t; }
+  }
+  uint32_t* ids = kout;  // free now
+  for (int i = lane; i < n; i += 32) ids[i] = src[iin[i]].y;
+  __syncwarp();
+  // equal depths: ascending id (odd-even transposition restricted to runs of identical keys)
+  for (;;) {
+    bool changed = false;
+#pragma unroll
+    for (int phase = 0; phase < 2; phase++) {
+      for (int i = 2 * lane + phase; i + 1 < n; i += 64) {
+        if (kin[i] == kin[i + 1]) {
+          const uint32_t a = ids[i], b = ids[i + 1];
+          if (a > b) { ids[i] = b; ids[i + 1] = a; changed = true; }
+        }
+      }
+      __syncwarp();
+    }
+    if (!__any_sync(0xffffffffu, changed)) break;
+  }
+  for (int i = lane; i < n; i += 32) dst[i] = ids[i];
+  __syncwarp();
+}
+
+// Large class: tiles with >= 2048 entries (the first n_large of tile_order), one CTA per SM, 201 KB of shared memory.
 template <int CAP, int THREADS>
-__global__ void __launch_bounds__(THREADS) sort_tiles_kernel(const Ctx cx, const int lo, const int hi) {
+__global__ void __launch_bounds__(THREADS) sort_tiles_kernel(const Ctx cx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  for (int t = blockIdx.x; t < cx.tiles; t += gridDim.x) {
+  const int n_large = (int)(cx.status->reserved[0] & 0xffffffffull);
+  for (int t = blockIdx.x; t < n_large; t += gridDim.x) {
     const uint2 r = cx.ranges[cx.tile_order[t]];  // longest lists first
     const int n = (int)(r.y - r.x);
-    if (n <= lo || n > hi) continue;
     const uint2* src = cx.keys + r.x;
     uint32_t* dst = cx.dup_ids + r.x;
-    if (n == 1) {
-      if (threadIdx.x == 0) dst[0] = src[0].y;
-      continue;
-    }
-    if (n <= SORT_BITONIC_MAX) {
-      unsigned long long* skeys = reinterpret_cast<unsigned long long*>(smem_raw);
-      int npow2 = 2;
-      while (npow2 < n) npow2 <<= 1;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint2 kv = src[i];
-        skeys[i] = ((unsigned long long)kv.x << 32) | kv.y;
-      }
-      __syncthreads();
-      bitonic_sort(skeys, n, npow2);
-      for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (uint32_t)skeys[i];
+    if (n <= 0) continue;
+    if (n <= 32) {
+      if (threadIdx.x < 32) warp_sort_tile(src, dst, n, smem_raw);
       __syncthreads();
     } else if (n <= CAP) {
       radix_sort_tile<CAP, THREADS>(src, dst, n, smem_raw);
@@ -361,6 +476,42 @@ __global__ void __launch_bounds__(THREADS) sort_tiles_kernel(const Ctx cx, const
       __syncthreads();
     }
   }
+}
+
+// One launch for every tile below SORT_SMALL entries.  tile_order is sorted by floor(log2 n) descending and the scan
+// kernel publishes how many tiles have n >= 2048 and n >= 512 (B2RStatus.reserved[0]), so CTA b knows its job without
+// searching: the first CTAs take one 512..2047-entry tile each (CTA-wide radix sort), the rest take eight shorter
+// tiles each, one per warp.  The grid is sized for the worst case; surplus CTAs exit at once.
+template <int CAP, int THREADS>
+__global__ void __launch_bounds__(THREADS) sort_mixed_kernel(const Ctx cx) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  B2R_TRACE_BEGIN();
+  const unsigned long long cls = cx.status->reserved[0];
+  const int n_large = (int)(cls & 0xffffffffull), n_ge512 = (int)(cls >> 32);
+  const int n_cta = n_ge512 - n_large;
+  const int b = blockIdx.x;
+  if (b < n_cta) {
+    const uint2 r = cx.ranges[cx.tile_order[n_large + b]];
+    const int n = (int)(r.y - r.x);  // < 2048; can be below 512 when the duplicate capacity clamped the range
+    const uint2* src = cx.keys + r.x;
+    uint32_t* dst = cx.dup_ids + r.x;
+    if (n > 32) {
+      radix_sort_tile<CAP, THREADS>(src, dst, n, smem_raw);
+    } else if (threadIdx.x < 32) {
+      warp_sort_tile(src, dst, n, smem_raw);
+    }
+    B2R_TRACE_END(n);
+    return;
+  }
+  const int warp = threadIdx.x >> 5;
+  const int t = n_ge512 + (b - n_cta) * (THREADS / 32) + warp;
+  int n = 0;
+  if (t < cx.tiles) {
+    const uint2 r = cx.ranges[cx.tile_order[t]];
+    n = (int)(r.y - r.x);
+    warp_sort_tile(cx.keys + r.x, cx.dup_ids + r.x, n, smem_raw + (size_t)warp * WSORT_BYTES);
+  }
+  B2R_TRACE_END(-n);
 }
 
 constexpr int SORT_SMALL = 2048;   // 256 threads, 28 KB of shared memory: several CTAs per SM
@@ -388,21 +539,32 @@ int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t 
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
     if (sms <= 0) sms = 148;
   }
-#ifndef B2_SORT_SMALL_THREADS
-#define B2_SORT_SMALL_THREADS 256
-#endif
-  constexpr int ST = B2_SORT_SMALL_THREADS;
-  constexpr size_t small_bytes = RadixSmem<SORT_SMALL, ST>::bytes, large_bytes = RadixSmem<SORT_LARGE, 512>::bytes;
-  cudaFuncSetAttribute(sort_tiles_kernel<SORT_LARGE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)large_bytes);
+  constexpr int ST = 256;
+  constexpr size_t cta_bytes = RadixSmem<SORT_SMALL, ST>::bytes, warp_bytes = (ST / 32) * WSORT_BYTES;
+  constexpr size_t small_bytes = cta_bytes > warp_bytes ? cta_bytes : warp_bytes;
+  constexpr size_t large_bytes = RadixSmem<SORT_LARGE, 512>::bytes;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaFuncSetAttribute(sort_mixed_kernel<SORT_SMALL, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes);
+    cudaFuncSetAttribute(sort_tiles_kernel<SORT_LARGE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)large_bytes);
+    attr_set = true;
+  }
   {
     ProfScope p(K_SORT_SMALL, st);
-    launch_k(sort_tiles_kernel<SORT_SMALL, ST>, cx.tiles, ST, small_bytes, st, true, cx, 0, SORT_SMALL);
+    // worst case: every tile in the CTA class needs a CTA of its own (then there are no warp-class tiles left)
+    launch_k(sort_mixed_kernel<SORT_SMALL, ST>, cx.tiles, ST, small_bytes, st, true, cx);
   }
   {
     ProfScope p(K_SORT_LARGE, st);
-    launch_k(sort_tiles_kernel<SORT_LARGE, 512>, cx.tiles < sms ? cx.tiles : sms, 512, large_bytes, st, true, cx, SORT_SMALL, 0x7fffffff);
+    launch_k(sort_tiles_kernel<SORT_LARGE, 512>, cx.tiles < sms ? cx.tiles : sms, 512, large_bytes, st, true, cx);
   }
   return check_launch();
 }
 
 }  // namespace b2r
+
+#ifdef B2R_CTA_TRACE
+extern "C" int b2r_debug_trace_sort(unsigned long long* buf) {
+  return (int)cudaMemcpyToSymbol(b2r::g_cta_trace, &buf, sizeof(buf));
+}
+#endif

@@ -209,6 +209,8 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx) {
       bin_cursor[b] = run;
       run += c;
     }
+    // class boundaries of the per-tile sort (binning.cu): bins 0..20 hold n >= 2048, bins 0..22 hold n >= 512
+    cx.status->reserved[0] = (unsigned long long)bin_cursor[21] | ((unsigned long long)bin_cursor[23] << 32);
   }
   __syncthreads();
   for (int t = threadIdx.x; t < cx.tiles; t += blockDim.x) {

@@ -75,17 +75,19 @@ def main():
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     tf = torch.zeros(tiles * 4, 4, dtype=torch.int64, device=dev)
     tb = torch.zeros(tiles * 4, 4, dtype=torch.int64, device=dev)
-    for fn, t in (("b2r_debug_trace_fwd", tf), ("b2r_debug_trace_bwd", tb)):
+    ts = torch.zeros(tiles * 4, 4, dtype=torch.int64, device=dev)
+    for fn, t in (("b2r_debug_trace_fwd", tf), ("b2r_debug_trace_bwd", tb), ("b2r_debug_trace_sort", ts)):
         f = getattr(lib, fn)
         f.argtypes = [C.c_void_p]
         f.restype = C.c_int
         assert f(t.data_ptr()) == 0
     for _ in range(3):
-        tf.zero_(); tb.zero_()
+        tf.zero_(); tb.zero_(); ts.zero_()
         plan.forward(sc)
         if wl.backward:
             plan.backward(sc, gi, views)
     torch.cuda.synchronize()
+    report("sort_mixed (n > 0: CTA class, n < 0: -n of the last warp of a warp-class CTA)", ts.cpu().numpy())
     report("composite_fwd", tf.cpu().numpy())
     if wl.backward:
         report("composite_bwd", tb.cpu().numpy())
