@@ -21,6 +21,7 @@ int validate_scene(const B2RScene* sc) {
     if (sc->shs) {
       if (sc->sh_degree < 0 || sc->sh_degree > 3) return B2R_E_INVALID;
       if (sc->sh_coeffs < (sc->sh_degree + 1) * (sc->sh_degree + 1)) return B2R_E_INVALID;
+      if (sc->sh_coeffs > 16) return B2R_E_INVALID;  // rows are staged through shared memory (project.cu)
     }
   }
   return B2R_OK;

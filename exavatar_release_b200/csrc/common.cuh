@@ -206,6 +206,67 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};\n" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Warp-cooperative staging of 32 consecutive rows of L floats (SH coefficients / their gradients) between global and
+// shared memory.  Global side: the rows are one contiguous block, moved with full-line accesses and all loads of a
+// lane in flight together.  Shared side: row stride S = L | 1 (odd), so "every lane reads its own row" is conflict-free.
+// mode 0: shared <- global;  1: global <- shared;  2: global += shared.  `row_mask` (modes 1, 2) selects rows.
+// ---------------------------------------------------------------------------------------------------------------
+template <int MODE>
+__device__ __forceinline__ void stage_rows(float* __restrict__ wstage, float* __restrict__ gptr, const int L, const int nrows,
+                                           const unsigned row_mask) {
+  const int lane = threadIdx.x & 31;
+  const int S = L | 1;
+  if (L == 48 && (reinterpret_cast<uintptr_t>(gptr) & 15) == 0) {  // degree-3 layout: 12 float4 per row
+    float4* g4 = reinterpret_cast<float4*>(gptr);
+    const int n4 = nrows * 12;
+    float4 v[12];
+    if (MODE != 1) {
+#pragma unroll
+      for (int u = 0; u < 12; u++) {
+        const int j = lane + 32 * u;
+        v[u] = j < n4 ? (MODE == 0 ? __ldg(g4 + j) : g4[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 12; u++) {
+      const int j = lane + 32 * u;
+      const int r = j / 12, c = (j - r * 12) * 4;
+      float* w = wstage + r * S + c;
+      if (j < n4) {
+        if (MODE == 0) {
+          w[0] = v[u].x; w[1] = v[u].y; w[2] = v[u].z; w[3] = v[u].w;
+        } else if ((row_mask >> r) & 1u) {
+          if (MODE == 1) g4[j] = make_float4(w[0], w[1], w[2], w[3]);
+          else g4[j] = make_float4(v[u].x + w[0], v[u].y + w[1], v[u].z + w[2], v[u].w + w[3]);
+        }
+      }
+    }
+    return;
+  }
+  const int total = nrows * L;
+  for (int e0 = lane; e0 < total; e0 += 32 * 8) {
+    float v[8];
+    if (MODE != 1) {
+#pragma unroll
+      for (int u = 0; u < 8; u++) {
+        const int e = e0 + 32 * u;
+        v[u] = e < total ? gptr[e] : 0.f;
+      }
+    }
+#pragma unroll
+    for (int u = 0; u < 8; u++) {
+      const int e = e0 + 32 * u;
+      if (e < total) {
+        const int r = e / L, c = e - r * L;
+        float* w = wstage + r * S + c;
+        if (MODE == 0) *w = v[u];
+        else if ((row_mask >> r) & 1u) gptr[e] = MODE == 1 ? *w : v[u] + *w;
+      }
+    }
+  }
+}
+
 // launch wrappers (one per translation unit)
 int launch_project(const B2RScene& sc, const Ctx& cx, int32_t* radii, cudaStream_t st);
 int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t st);

@@ -25,7 +25,7 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh,
   clamp_bits = 0;
 #pragma unroll
   for (int c = 0; c < 3; c++) {
-    auto SH = [&](int k) { return __ldg(sh + k * 3 + c); };
+    auto SH = [&](int k) { return sh[k * 3 + c]; };  // `sh` is the Gaussian's row in the warp's shared-memory stage
     float r = B2R_SH_C0 * SH(0);
     if (deg > 0) {
       r = r - B2R_SH_C1 * y * SH(1) + B2R_SH_C1 * z * SH(2) - B2R_SH_C1 * x * SH(3);
@@ -57,6 +57,19 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
     __syncthreads();
   }
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  // SH rows (192 bytes apart for degree 3) are staged through shared memory: each warp copies the contiguous block of
+  // its 32 rows with coalesced 128-byte loads; a thread then reads its own row (odd row stride: conflict-free).
+  const float* shrow = nullptr;
+  if (sc.shs) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int L = sc.sh_coeffs * 3, S = L | 1;
+    float* wstage = reinterpret_cast<float*>(s_cnt + (aggregate ? cx.tiles : 0)) + (size_t)warp * 32 * S;
+    const int row0 = blockIdx.x * blockDim.x + warp * 32;
+    const int nrows = min(32, sc.P - row0);
+    if (nrows > 0) stage_rows<0>(wstage, const_cast<float*>(sc.shs) + (size_t)row0 * L, L, nrows, 0xffffffffu);
+    __syncwarp();
+    shrow = wstage + lane * S;
+  }
   const Cam cam = load_cam(sc);
   bool visible = false;
   Geom g;
@@ -105,7 +118,7 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
           float rgb[3];
           uint32_t bits = 0;
           if (sc.shs) {
-            sh_to_rgb(sc.sh_degree, sc.shs + (size_t)i * sc.sh_coeffs * 3, p, cam, rgb, bits);
+            sh_to_rgb(sc.sh_degree, shrow, p, cam, rgb, bits);
           } else {
             rgb[0] = __ldg(sc.colors_precomp + 3 * (size_t)i);
             rgb[1] = __ldg(sc.colors_precomp + 3 * (size_t)i + 1);
@@ -259,9 +272,15 @@ int launch_project(const B2RScene& sc, const Ctx& cx, int32_t* radii, cudaStream
   { ProfScope p(K_MISC, st); launch_k(status_reset_kernel, (cx.tiles + 1023) / 1024, 1024, 0, st, true, cx); }
   if (sc.P > 0) {
     ProfScope p(K_PROJECT, st);
-    const size_t smem = (size_t)cx.tiles * 4;
     const int aggregate = cx.tiles <= 2048;  // beyond that the per-CTA sweeps over the tile table cost more than they save
-    launch_k(project_kernel, (sc.P + 255) / 256, 256, aggregate ? smem : 0, st, true, sc, cx, radii, aggregate);
+    const size_t smem = (aggregate ? (size_t)cx.tiles * 4 : 0) +
+                        (sc.shs ? (size_t)8 * 32 * ((sc.sh_coeffs * 3) | 1) * sizeof(float) : 0);
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+      attr_set = true;
+    }
+    launch_k(project_kernel, (sc.P + 255) / 256, 256, smem, st, true, sc, cx, radii, aggregate);
   }
   { ProfScope p(K_TILE_SCAN, st); launch_k(tile_scan_kernel, 1, 1024, 0, st, true, cx); }
   return check_launch();

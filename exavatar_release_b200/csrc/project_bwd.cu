@@ -11,15 +11,13 @@
 
 namespace b2r {
 
-__global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, const Ctx cx, const B2RBackwardArgs out,
-                                                          const float* __restrict__ gacc) {
-  const int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= sc.P) return;
+// Body of K6 for one Gaussian.  `shrow` (shared memory, may be null) holds the Gaussian's SH coefficients on entry and
+// its SH gradient on exit (row layout k*3 + c, as in global memory); see the staging in the kernel below.
+__device__ __forceinline__ void project_bwd_one(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& out,
+                                                const float* __restrict__ gacc, const int i, const bool visible,
+                                                const int4 aux, float* shrow) {
   const int M = sc.sh_coeffs;
-  const int4 aux = cx.aux[i];
-  const bool visible = aux.z > 0;
   const bool accumulate = (out.flags & B2R_BWD_ACCUMULATE) != 0;
-  if (accumulate && !visible) return;  // nothing to add
 
   float dm[3] = {0.f, 0.f, 0.f}, dm2[2] = {0.f, 0.f}, dcol[3] = {0.f, 0.f, 0.f}, dop = 0.f;
   float dS[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
@@ -141,13 +139,11 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
     }
   }
 
-  // ---- SH (App. A.7): writes dL/dshs and adds the view-direction term to dL/dmean ----
-  if (sc.shs && out.dL_dshs) {
-    float* dsh = out.dL_dshs + (size_t)i * M * 3;
+  // ---- SH (App. A.7): dL/dshs replaces the coefficients in `shrow`; the view-direction term is added to dL/dmean ----
+  if (shrow) {
     if (!visible) {
-      for (int k = 0; k < M * 3; k++) dsh[k] = 0.f;
+      for (int k = 0; k < M * 3; k++) shrow[k] = 0.f;
     } else {
-      const float* sh = sc.shs + (size_t)i * M * 3;
       const int deg = sc.sh_degree;
       const int used = (deg + 1) * (deg + 1);
       const float ddx = p.x - cam.campos[0], ddy = p.y - cam.campos[1], ddz = p.z - cam.campos[2];
@@ -158,10 +154,11 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
 #pragma unroll
       for (int c = 0; c < 3; c++) {
         const float gc = ((clamp_bits >> c) & 1u) ? 0.f : dcol[c];
-        auto SH = [&](int k) { return __ldg(sh + k * 3 + c); };
-        auto DSH = [&](int k, float basis) {
-          if (accumulate) dsh[k * 3 + c] += basis * gc; else dsh[k * 3 + c] = basis * gc;
-        };
+        float shv[16];  // this channel's coefficients, read before the gradient overwrites them in place
+#pragma unroll
+        for (int k = 0; k < 16; k++) shv[k] = k < used ? shrow[k * 3 + c] : 0.f;
+        auto SH = [&](int k) { return shv[k]; };
+        auto DSH = [&](int k, float basis) { shrow[k * 3 + c] = basis * gc; };
         float drx = 0.f, dry = 0.f, drz = 0.f;
         DSH(0, B2R_SH_C0);
         if (deg > 0) {
@@ -193,7 +190,7 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
             }
           }
         }
-        if (!accumulate) for (int k = used; k < M; k++) dsh[k * 3 + c] = 0.f;
+        for (int k = used; k < M; k++) shrow[k * 3 + c] = 0.f;
         ddir[0] += drx * gc;
         ddir[1] += dry * gc;
         ddir[2] += drz * gc;
@@ -239,9 +236,54 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
   }
 }
 
+// K6.  The per-Gaussian body above reads / writes everything with one thread per Gaussian, which is fine for the
+// 3..4-float rows but not for SH: (P,16,3) rows are 192 bytes apart, so a per-thread walk touches 32 different
+// 128-byte lines per load instruction.  SH rows therefore move through shared memory: every warp copies the
+// contiguous block of its 32 rows in with coalesced 128-byte accesses (odd row stride: conflict-free), the body
+// turns each row into its gradient in place, and the warp writes (or accumulates) the block back the same way.
+__global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, const Ctx cx, const B2RBackwardArgs out,
+                                                          const float* __restrict__ gacc) {
+  extern __shared__ float sh_stage[];
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool in_range = i < sc.P;
+  const bool accumulate = (out.flags & B2R_BWD_ACCUMULATE) != 0;
+  int4 aux = make_int4(0, 0, 0, 0);
+  if (in_range) aux = cx.aux[i];
+  const bool visible = aux.z > 0;
+  const bool active = in_range && !(accumulate && !visible);  // an invisible Gaussian has nothing to add
+  const bool use_sh = sc.shs != nullptr && out.dL_dshs != nullptr;
+  const int L = sc.sh_coeffs * 3, S = L | 1;
+  float* wstage = sh_stage + (size_t)warp * 32 * S;
+  const int row0 = blockIdx.x * blockDim.x + warp * 32;
+  const int nrows = min(32, sc.P - row0);
+  if (use_sh && nrows > 0) {
+    stage_rows<0>(wstage, const_cast<float*>(sc.shs) + (size_t)row0 * L, L, nrows, 0xffffffffu);
+    __syncwarp();
+  }
+  float* shrow = use_sh ? wstage + lane * S : nullptr;
+  if (active) project_bwd_one(sc, cx, out, gacc, i, visible, aux, shrow);
+  if (use_sh && nrows > 0) {
+    const unsigned rows_active = __ballot_sync(0xffffffffu, active);
+    __syncwarp();  // every lane's row is complete before the block is written out cooperatively
+    float* dst = out.dL_dshs + (size_t)row0 * L;
+    if (accumulate) stage_rows<2>(wstage, dst, L, nrows, rows_active);
+    else stage_rows<1>(wstage, dst, L, nrows, rows_active);
+  }
+}
+
 int launch_project_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, const float* gacc, cudaStream_t st) {
   ProfScope p(K_PROJECT_BWD, st, sc.P > 0 ? 1 : 0);
-  if (sc.P > 0) launch_k(project_bwd_kernel, (sc.P + 255) / 256, 256, 0, st, true, sc, cx, a, gacc);
+  if (sc.P > 0) {
+    const bool use_sh = sc.shs != nullptr && a.dL_dshs != nullptr;
+    const size_t smem = use_sh ? (size_t)8 * 32 * ((sc.sh_coeffs * 3) | 1) * sizeof(float) : 0;
+    static bool attr_set = false;
+    if (!attr_set) {
+      cudaFuncSetAttribute(project_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      attr_set = true;
+    }
+    launch_k(project_bwd_kernel, (sc.P + 255) / 256, 256, smem, st, true, sc, cx, a, gacc);
+  }
   return check_launch();
 }
 

@@ -17,6 +17,7 @@ from torch import nn
 
 from .camera import get_fov, get_proj_matrix, get_view_matrix
 from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
+from .sh import sh_to_rgb
 
 
 def render_settings(img_shape, cam_param, bg, settings_cls=GaussianRasterizationSettings):
@@ -63,11 +64,17 @@ class GaussianRenderer(nn.Module):
         mean_2d.requires_grad = True
         mean_2d.retain_grad()
 
+        # Reference call: colours precomputed by the caller (module.py:635-636).  SURVEY.md section 8f-4: assets that carry
+        # `shs` (P, M, 3) + `sh_degree` instead of `rgb` are coloured inside the projection kernel.
+        shs = gaussian_assets.get("shs") if "rgb" not in gaussian_assets else None
+        if shs is not None:
+            rasterizer = self.rasterizer_cls(raster_settings=raster_settings._replace(sh_degree=int(gaussian_assets["sh_degree"])))
+
         render_img, radius, render_depthmap, render_mask = rasterizer(
             means3D=mean_3d,
             means2D=mean_2d,
-            shs=None,
-            colors_precomp=gaussian_assets["rgb"],
+            shs=shs,
+            colors_precomp=None if shs is not None else gaussian_assets["rgb"],
             opacities=gaussian_assets["opacity"],
             scales=gaussian_assets["scale"],
             rotations=gaussian_assets["rotation"],
@@ -79,3 +86,24 @@ class GaussianRenderer(nn.Module):
                 "mean_2d": mean_2d,
                 "is_vis": radius > 0,
                 "radius": radius}
+
+
+def scene_gaussian_assets(mean, opacity_logit, log_scale, rotation, feature_dc, feature_rest, active_sh_degree, cam_param,
+                          in_kernel_sh: bool = False):
+    """The asset dict `SceneGaussian.forward` hands to the renderer (module.py:253-272): sigmoid opacity, exp scale,
+    SH coefficients `cat(feature_dc, feature_rest)` (P, 16, 3).  `rotation` is the activated quaternion (the reference
+    derives it from a 6-D parametrisation with pytorch3d, which is outside this path).
+
+    in_kernel_sh=False reproduces the reference: view direction, SH polynomial and clamp in PyTorch -> `rgb`.
+    in_kernel_sh=True   passes `shs` + `sh_degree` through; the rasteriser evaluates the same
+    polynomial per Gaussian in its projection kernel and back-propagates to the coefficients and, through the view
+    direction, to the mean -- no (P,16,3)->(P,3) PyTorch kernels, no (P,3) colour round trip through HBM."""
+    sh = torch.cat((feature_dc, feature_rest), 1)
+    assets = {"mean_3d": mean, "opacity": torch.sigmoid(opacity_logit), "scale": torch.exp(log_scale), "rotation": rotation}
+    if in_kernel_sh:
+        assets["shs"] = sh
+        assets["sh_degree"] = int(active_sh_degree)
+    else:
+        cam_pos = torch.matmul(torch.inverse(cam_param["R"]), -cam_param["t"].view(3, 1)).view(1, 3)
+        assets["rgb"] = sh_to_rgb(int(active_sh_degree), sh, mean, cam_pos.to(mean.dtype))
+    return assets
