@@ -57,6 +57,9 @@ def parse():
                     help="e2e leg: copy the Gaussian set host->device once per step (the frames of a step share it, as in "
                          "the device-resident leg; result = losses + the step's summed gradients) or once per frame "
                          "(every rasteriser call gets fresh host inputs and returns its own gradients)")
+    ap.add_argument("--five-render", action="store_true",
+                    help="extra leg: ExAvatar's five-render training frame (model.py:81-162) on FiveRenderPlan; needs a "
+                         "workload with both populations (C2, C4)")
     ap.add_argument("--trace-e2e", default=None, help="write a chrome trace (CUPTI via torch.profiler) of one e2e step here")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU budget of the cpu_baseline leg")
     return ap.parse_args()
@@ -569,6 +572,56 @@ def run_b200(args):
                          else "eager, copies on side streams"),
                "steps": ke}
 
+    # ---- optional leg: the five-render training frame of avatar/main/model.py:81-162 ----
+    five = None
+    if args.five_render and wl.backward and wl.n_avatar and wl.n_scene and not use_sh:
+        from exavatar_release_b200.plan import RENDERS, FiveRenderPlan
+        from exavatar_release_b200.synthetic import make_population_assets
+        scene_a, human_a, refined_a = make_population_assets(args.workload, seed=0, device=dev)
+        bg_rand = torch.tensor([0.3, 0.7, 0.2], device=dev)
+        st_w = [render_settings((H, Wd), c, bg) for c in cams]
+        st_r = [render_settings((H, Wd), c, bg_rand) for c in cams]
+        g5 = [{r: make_grad_image(args.workload, seed=10 * f + j, device=dev) for j, r in enumerate(RENDERS)} for f in range(F)]
+        probe = FiveRenderPlan(wl.n_scene, wl.n_avatar, Wd, H, {r: 8_000_000 for r in RENDERS}, dev)
+        probe.set_scene(scene_a)
+        need = {r: 0 for r in RENDERS}
+        for f in range(F):
+            probe.frame(f, st_w[f], st_r[f], scene_a, human_a, refined_a, g5[f], accumulate=False)
+            torch.cuda.synchronize(dev)
+            for r in RENDERS:
+                need[r] = max(need[r], probe.plans[r].status()["num_dups"])
+        del probe
+        fplan = FiveRenderPlan(wl.n_scene, wl.n_avatar, Wd, H, {r: int(need[r] * 1.1) + 4096 for r in RENDERS}, dev)
+
+        def five_body():
+            fplan.set_scene(scene_a)
+            for f in range(F):
+                fplan.frame(f, st_w[f], st_r[f], scene_a, human_a, refined_a, g5[f], accumulate=(f > 0))
+            return fplan.reduce()
+
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            five_body()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        g5graph = torch.cuda.CUDAGraph()
+        l0 = lib.b2r_launch_count()
+        with torch.cuda.graph(g5graph):
+            five_out = five_body()
+        five_launches = lib.b2r_launch_count() - l0
+        for _ in range(3):
+            g5graph.replay()
+        k5 = max(3, min(K, 10))
+        ms5, _, _ = timed(g5graph.replay, k5)
+        if fplan.overflowed():
+            raise SystemExit("bench.py: five-render leg overflowed its duplicate capacity")
+        five = {"value": world * F * k5 / (ms5 * 1e-3), "unit": "frames/s (5 renders, fwd+bwd, per frame)",
+                "renders_per_s": 5 * world * F * k5 / (ms5 * 1e-3), "launches_per_step": int(five_launches),
+                "P_scene": wl.n_scene, "P_human": wl.n_avatar, "dups_per_render": need,
+                "pattern": "scene | human (random bg) | cat(scene.detach(), human) | human_refined | "
+                           "cat(scene.detach(), human_refined); five streams per frame, one CUDA graph per step"}
+
     # ---- leg 4: CPU baseline on the host cores (rank 0) ----
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -589,7 +642,7 @@ def run_b200(args):
                 "dtype": "f32", "data": "synthetic",
                 "config": config_dict(args, wl, {"cuda_graph": graph is not None, "dup_capacity": cap, "lanes": S,
                                                  "frames_per_rank_per_step": F}),
-                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu,
+                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "five_render": five,
                 "wall_s_timed_region": wall}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -52,7 +52,7 @@ class B2RBackwardArgs(C.Structure):
         ("dL_dcolor", _fp), ("dL_ddepth", _fp), ("dL_dalpha", _fp),
         ("dL_dmeans3D", _fp), ("dL_dmeans2D", _fp), ("dL_dshs", _fp), ("dL_dcolors", _fp), ("dL_dopacities", _fp),
         ("dL_dscales", _fp), ("dL_drotations", _fp), ("dL_dcov3D", _fp),
-        ("flags", C.c_uint32), ("reserved", C.c_uint32),
+        ("flags", C.c_uint32), ("first_row", C.c_uint32),
         ("densify_grad_accum", _fp), ("densify_count", _fp), ("densify_radius_max", _fp),
     ]
 

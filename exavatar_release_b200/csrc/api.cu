@@ -120,6 +120,7 @@ int b2r_backward(const B2RScene* scene, const B2RWorkspace* ws, const B2RBackwar
   if (!args || !args->dL_dcolor || !bwd_scratch) return B2R_E_INVALID;
   if (bwd_scratch_bytes < b2r_backward_scratch_bytes(scene->P)) return B2R_E_WORKSPACE;
   if (scene->shs && args->dL_dshs == nullptr && scene->P > 0) return B2R_E_INVALID;
+  if ((int64_t)args->first_row > (int64_t)scene->P) return B2R_E_INVALID;
   const Ctx cx = resolve(ws, scene->P, scene->width, scene->height);
   float* gacc = (float*)bwd_scratch;
   rc = launch_composite_bwd(*scene, cx, *args, gacc, (cudaStream_t)stream);

@@ -14,8 +14,8 @@ namespace b2r {
 // Body of K6 for one Gaussian.  `shrow` (shared memory, may be null) holds the Gaussian's SH coefficients on entry and
 // its SH gradient on exit (row layout k*3 + c, as in global memory); see the staging in the kernel below.
 __device__ __forceinline__ void project_bwd_one(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& out,
-                                                const float* __restrict__ gacc, const int i, const bool visible,
-                                                const int4 aux, float* shrow) {
+                                                const float* __restrict__ gacc, const int i, const size_t oi,
+                                                const bool visible, const int4 aux, float* shrow) {
   const int M = sc.sh_coeffs;
   const bool accumulate = (out.flags & B2R_BWD_ACCUMULATE) != 0;
 
@@ -202,12 +202,12 @@ __device__ __forceinline__ void project_bwd_one(const B2RScene& sc, const Ctx& c
     }
   }
 
-  if (visible && out.densify_grad_accum) out.densify_grad_accum[i] += sqrtf(dm2[0] * dm2[0] + dm2[1] * dm2[1]);
-  if (visible && out.densify_count) out.densify_count[i] += 1.f;
-  if (visible && out.densify_radius_max) out.densify_radius_max[i] = fmaxf(out.densify_radius_max[i], (float)aux.z);
+  if (visible && out.densify_grad_accum) out.densify_grad_accum[oi] += sqrtf(dm2[0] * dm2[0] + dm2[1] * dm2[1]);
+  if (visible && out.densify_count) out.densify_count[oi] += 1.f;
+  if (visible && out.densify_radius_max) out.densify_radius_max[oi] = fmaxf(out.densify_radius_max[oi], (float)aux.z);
   auto put3 = [&](float* base, const float* v) {
     if (!base) return;
-    float* d = base + 3 * (size_t)i;
+    float* d = base + 3 * oi;
     if (accumulate) { d[0] += v[0]; d[1] += v[1]; d[2] += v[2]; }
     else { d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; }
   };
@@ -217,19 +217,19 @@ __device__ __forceinline__ void project_bwd_one(const B2RScene& sc, const Ctx& c
   put3(out.dL_dcolors, dcol);
   put3(out.dL_dscales, dscale);
   if (out.dL_dopacities) {
-    if (accumulate) out.dL_dopacities[i] += dop; else out.dL_dopacities[i] = dop;
+    if (accumulate) out.dL_dopacities[oi] += dop; else out.dL_dopacities[oi] = dop;
   }
   if (out.dL_drotations) {
 #pragma unroll
     for (int k = 0; k < 4; k++) {
-      float* d = out.dL_drotations + 4 * (size_t)i + k;
+      float* d = out.dL_drotations + 4 * oi + k;
       if (accumulate) *d += dq[k]; else *d = dq[k];
     }
   }
   if (out.dL_dcov3D) {
 #pragma unroll
     for (int k = 0; k < 6; k++) {
-      float* d = out.dL_dcov3D + 6 * (size_t)i + k;
+      float* d = out.dL_dcov3D + 6 * oi + k;
       const float v = sc.cov3D_precomp ? dS[k] : 0.f;
       if (accumulate) *d += v; else *d = v;
     }
@@ -251,7 +251,10 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
   int4 aux = make_int4(0, 0, 0, 0);
   if (in_range) aux = cx.aux[i];
   const bool visible = aux.z > 0;
-  const bool active = in_range && !(accumulate && !visible);  // an invisible Gaussian has nothing to add
+  // out.first_row: Gaussians below it are a detached prefix (ExAvatar renders cat(scene.detach(), human),
+  // model.py:117-125): nothing is written for them and Gaussian i lands in output row i - first_row
+  const int first_row = (int)out.first_row;
+  const bool active = in_range && i >= first_row && !(accumulate && !visible);  // an invisible Gaussian has nothing to add
   const bool use_sh = sc.shs != nullptr && out.dL_dshs != nullptr;
   const int L = sc.sh_coeffs * 3, S = L | 1;
   float* wstage = sh_stage + (size_t)warp * 32 * S;
@@ -262,11 +265,11 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
     __syncwarp();
   }
   float* shrow = use_sh ? wstage + lane * S : nullptr;
-  if (active) project_bwd_one(sc, cx, out, gacc, i, visible, aux, shrow);
+  if (active) project_bwd_one(sc, cx, out, gacc, i, (size_t)(i - first_row), visible, aux, shrow);
   if (use_sh && nrows > 0) {
     const unsigned rows_active = __ballot_sync(0xffffffffu, active);
     __syncwarp();  // every lane's row is complete before the block is written out cooperatively
-    float* dst = out.dL_dshs + (size_t)row0 * L;
+    float* dst = out.dL_dshs + ((ptrdiff_t)row0 - first_row) * L;  // rows below first_row are masked off, never touched
     if (accumulate) stage_rows<2>(wstage, dst, L, nrows, rows_active);
     else stage_rows<1>(wstage, dst, L, nrows, rows_active);
   }

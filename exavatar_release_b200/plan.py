@@ -62,14 +62,16 @@ class FramePlan:
 
     def backward(self, sc, g_color: torch.Tensor, grads: Dict[str, Optional[torch.Tensor]], accumulate: bool = False,
                  g_depth: Optional[torch.Tensor] = None, g_alpha: Optional[torch.Tensor] = None,
-                 densify: Optional[Dict[str, torch.Tensor]] = None) -> None:
+                 densify: Optional[Dict[str, torch.Tensor]] = None, first_row: int = 0) -> None:
         """grads keys: means3D, means2D, shs, colors, opacities, scales, rotations, cov3D (missing -> not written).
         densify (optional): {'grad_accum', 'count', 'radius_max'} fp32 (P) tensors updated in place by the backward
-        projection kernel -- ExAvatar's `track_stats` + `radius_max` update (module.py:155-157, model.py:283-285)."""
+        projection kernel -- ExAvatar's `track_stats` + `radius_max` update (module.py:155-157, model.py:283-285).
+        first_row: Gaussians [0, first_row) are a detached prefix (cat(scene.detach(), human), model.py:117-125): the
+        `grads` tensors then have P - first_row rows and receive the gradient of the remaining Gaussians only."""
         a = L.B2RBackwardArgs(_ptr(g_color), _ptr(g_depth), _ptr(g_alpha), _ptr(grads.get("means3D")),
                               _ptr(grads.get("means2D")), _ptr(grads.get("shs")), _ptr(grads.get("colors")),
                               _ptr(grads.get("opacities")), _ptr(grads.get("scales")), _ptr(grads.get("rotations")),
-                              _ptr(grads.get("cov3D")), L.B2R_BWD_ACCUMULATE if accumulate else 0, 0,
+                              _ptr(grads.get("cov3D")), L.B2R_BWD_ACCUMULATE if accumulate else 0, int(first_row),
                               _ptr((densify or {}).get("grad_accum")), _ptr((densify or {}).get("count")),
                               _ptr((densify or {}).get("radius_max")))
         with torch.cuda.device(self.device):
@@ -153,3 +155,82 @@ def _views_of(flat: torch.Tensor, P: int, sh_coeffs: int = 0):
         views[name] = flat[o:o + w * P].view(P, w) if name != "shs" else flat[o:o + w * P].view(P, sh_coeffs, 3)
         o += w * P
     return flat, views
+
+
+RENDERS = ("scene", "human", "scene_human", "human_refined", "scene_human_refined")
+
+
+class FiveRenderPlan:
+    """One ExAvatar training frame = five rasteriser calls with one camera (avatar/main/model.py:81-162):
+
+        scene                      -> gradients to the scene Gaussians
+        human            (bg rand) -> gradients to the human Gaussians
+        cat(scene.detach(), human) -> gradients to the human Gaussians only        (model.py:117-125)
+        human_refined    (bg rand) -> gradients to the refined human Gaussians
+        cat(scene.detach(), human_refined) -> gradients to the refined human Gaussians only
+
+    The reference runs them one after the other, each with its own device->host sync.  Here the five renders are
+    independent until their gradients meet, so each runs on its own CUDA stream (fork / join inside the caller's
+    stream: capturable in one CUDA graph with the rest of the step); the "detached prefix" of the combined renders is a
+    field of the backward call (`first_row`), so the human part of their gradient is written straight into a
+    human-sized bucket and nothing is computed-then-discarded on the host side.  Frames of a step accumulate into the
+    same five buckets; `reduce()` folds them into the three parameter sets (scene, human, human_refined).
+    """
+
+    def __init__(self, P_scene: int, P_human: int, width: int, height: int, caps: Dict[str, int], device):
+        self.Ps, self.Ph = int(P_scene), int(P_human)
+        self.device = torch.device(device)
+        sizes = {"scene": self.Ps, "human": self.Ph, "scene_human": self.Ps + self.Ph, "human_refined": self.Ph,
+                 "scene_human_refined": self.Ps + self.Ph}
+        self.plans = {r: FramePlan(sizes[r], width, height, caps[r], device) for r in RENDERS}
+        self.streams = {r: torch.cuda.Stream(self.device) for r in RENDERS}
+        self.first_row = {"scene": 0, "human": 0, "scene_human": self.Ps, "human_refined": 0, "scene_human_refined": self.Ps}
+        out_rows = {"scene": self.Ps, "human": self.Ph, "scene_human": self.Ph, "human_refined": self.Ph,
+                    "scene_human_refined": self.Ph}
+        self.flat, self.views = {}, {}
+        for r in RENDERS:
+            self.flat[r], self.views[r] = grad_bucket(out_rows[r], device)
+        f = lambda w: torch.empty(self.Ps + self.Ph, w, dtype=torch.float32, device=device)
+        widths = {"mean_3d": 3, "opacity": 1, "scale": 3, "rotation": 4, "rgb": 3}
+        self.cat = {r: {k: f(w) for k, w in widths.items()} for r in ("scene_human", "scene_human_refined")}
+
+    def set_scene(self, scene_assets: Dict[str, torch.Tensor]) -> None:
+        """Copies the (detached) scene Gaussians into the prefix of the two combined asset sets; once per step."""
+        for r in self.cat:
+            for k, buf in self.cat[r].items():
+                buf[: self.Ps].copy_(scene_assets[k].reshape(self.Ps, -1))
+
+    def assets_of(self, render: str, scene, human, refined):
+        if render == "scene":
+            return scene
+        if render in ("human", "human_refined"):
+            return human if render == "human" else refined
+        src = human if render == "scene_human" else refined
+        for k, buf in self.cat[render].items():
+            buf[self.Ps:].copy_(src[k].reshape(self.Ph, -1))
+        return self.cat[render]
+
+    def frame(self, key, settings, settings_human_bg, scene, human, refined, g_colors: Dict[str, torch.Tensor],
+              accumulate: bool) -> None:
+        """Forward + backward of the five renders of one frame.  `settings_human_bg` carries the random background of
+        the human-only renders (model.py:72).  `key` caches the per-(frame, render) scene descriptors."""
+        cur = torch.cuda.current_stream(self.device)
+        for r in RENDERS:
+            st = self.streams[r]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                plan = self.plans[r]
+                assets = self.assets_of(r, scene, human, refined)
+                sc = plan.scene((key, r), settings_human_bg if r in ("human", "human_refined") else settings, assets)
+                plan.forward(sc)
+                plan.backward(sc, g_colors[r], self.views[r], accumulate=accumulate, first_row=self.first_row[r])
+        for r in RENDERS:
+            cur.wait_stream(self.streams[r])
+
+    def reduce(self):
+        """(scene, human, human_refined) flat gradient buckets of the step."""
+        return (self.flat["scene"], self.flat["human"] + self.flat["scene_human"],
+                self.flat["human_refined"] + self.flat["scene_human_refined"])
+
+    def overflowed(self) -> bool:
+        return any(p.status()["overflow"] for p in self.plans.values())

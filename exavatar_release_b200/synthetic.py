@@ -106,3 +106,22 @@ def make_grad_image(workload, seed=0, device="cpu"):
     wl = WORKLOADS[workload] if isinstance(workload, str) else workload
     g = torch.Generator().manual_seed(1000 + seed)
     return torch.randn(3, wl.height, wl.width, generator=g).to(device)
+
+
+def make_population_assets(workload, seed=0, device="cpu", focal_ratio=1.465):
+    """The two populations of a workload as separate asset dicts, for ExAvatar's five-render training frame
+    (avatar/main/model.py:81-162): `scene` (SceneGaussian), `human` (HumanGaussian) and `human_refined` (the same
+    anchors with the pose-dependent mean / scale / colour offsets applied, module.py:531-534,561-562)."""
+    wl = WORKLOADS[workload] if isinstance(workload, str) else workload
+    g = torch.Generator().manual_seed(seed)
+    tan_x = wl.width / (2 * focal_ratio * wl.height)
+    tan_y = 1.0 / (2 * focal_ratio)
+    keys = ("mean_3d", "scale", "rotation", "opacity", "rgb")
+    human = dict(zip(keys, (t.contiguous() for t in _avatar(wl.n_avatar, g))))
+    scene = dict(zip(keys, (t.contiguous() for t in _scene(wl.n_scene, g, tan_x, tan_y))))
+    refined = {k: v.clone() for k, v in human.items()}
+    refined["mean_3d"] = human["mean_3d"] + 0.002 * torch.randn(wl.n_avatar, 3, generator=g)
+    refined["scale"] = human["scale"] * torch.exp(0.1 * torch.randn(wl.n_avatar, 1, generator=g))
+    refined["rgb"] = (human["rgb"] + 0.05 * torch.randn(wl.n_avatar, 3, generator=g)).clamp(0, 1)
+    to = lambda d: {k: v.to(device) for k, v in d.items()}
+    return to(scene), to(human), to(refined)

@@ -116,7 +116,10 @@ typedef struct B2RBackwardArgs {
   float* dL_dcov3D;     /* (P,6) */
   uint32_t flags;       /* B2R_BWD_ACCUMULATE: outputs += gradient instead of outputs = gradient, so the frames a rank
                            renders in one step sum into a single bucket that is all-reduced once */
-  uint32_t reserved;
+  uint32_t first_row;   /* Gaussians [0, first_row) are a DETACHED PREFIX: no gradient is written for them and Gaussian i
+                           goes to row i - first_row of every output (outputs then have P - first_row rows).  This is
+                           ExAvatar's "scene + human" render, cat(scene.detach(), human) (avatar/main/model.py:117-125):
+                           the human part of the gradient lands directly in the human bucket.  0 = off. */
   /* Optional fused densification bookkeeping, each (P) or NULL, updated IN PLACE for Gaussians
    * with radii > 0 exactly as ExAvatar does after backward (avatar/common/nets/module.py:155-157,
    * avatar/main/model.py:283-285):  grad_accum += ||dL/dmeans2D.xy||,  count += 1,  radius_max = max(radius_max, radii). */

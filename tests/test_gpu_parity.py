@@ -489,6 +489,56 @@ def test_unused_outputs_get_no_materialised_gradients(dev):
     assert float(lv1["rgb"].grad.abs().max()) == 0.0
 
 
+def test_five_render_plan_matches_the_reference_pattern(dev):
+    """FiveRenderPlan (five concurrent renders, detached scene prefix via `first_row`) == ExAvatar's pattern written
+    with the public autograd API: renderer(scene), renderer(human, bg), renderer(cat(scene.detach(), human)), and the
+    same two for the refined human (avatar/main/model.py:81-162), two frames accumulated."""
+    from exavatar_release_b200 import GaussianRenderer
+    from exavatar_release_b200.camera import look_at_cam_param
+    from exavatar_release_b200.plan import RENDERS, FiveRenderPlan
+    from exavatar_release_b200.renderer import render_settings
+    from exavatar_release_b200.synthetic import make_population_assets
+    rz = RZ()
+    wl = WORKLOADS["T1"]
+    H, W = wl.height, wl.width
+    scene, human, refined = make_population_assets("T1", seed=0, device=dev)
+    Ps, Ph = scene["mean_3d"].shape[0], human["mean_3d"].shape[0]
+    bg_w, bg_r = torch.ones(3, device=dev), torch.tensor([0.3, 0.7, 0.2], device=dev)
+    yaws = (-8.0, 11.0)
+    cams = [look_at_cam_param(y, (H, W), device=dev) for y in yaws]
+    gcol = [{r: make_grad_image("T1", 10 * f + j).to(dev) for j, r in enumerate(RENDERS)} for f in range(len(yaws))]
+
+    # reference pattern through the public API
+    lv = {n: {k: v.clone().requires_grad_() for k, v in a.items()} for n, a in (("scene", scene), ("human", human), ("refined", refined))}
+    R = GaussianRenderer()
+    cat = lambda a, b: {k: torch.cat((a[k].detach(), b[k])) for k in a}
+    loss = 0.0
+    for f, cam in enumerate(cams):
+        imgs = {"scene": R(lv["scene"], (H, W), cam)["img"], "human": R(lv["human"], (H, W), cam, bg_r)["img"],
+                "scene_human": R(cat(lv["scene"], lv["human"]), (H, W), cam)["img"],
+                "human_refined": R(lv["refined"], (H, W), cam, bg_r)["img"],
+                "scene_human_refined": R(cat(lv["scene"], lv["refined"]), (H, W), cam)["img"]}
+        loss = loss + sum((imgs[r] * gcol[f][r]).sum() for r in RENDERS)
+    loss.backward()
+
+    plan = FiveRenderPlan(Ps, Ph, W, H, {r: 2_000_000 for r in RENDERS}, dev)
+    plan.set_scene(scene)
+    for f, cam in enumerate(cams):
+        st_w = render_settings((H, W), cam, bg_w)
+        st_r = render_settings((H, W), cam, bg_r)
+        plan.frame(f, st_w, st_r, scene, human, refined, gcol[f], accumulate=(f > 0))
+    torch.cuda.synchronize()
+    assert not plan.overflowed()
+    names = {"mean_3d": "means3D", "opacity": "opacities", "scale": "scales", "rotation": "rotations", "rgb": "colors"}
+    from exavatar_release_b200.plan import _views_of
+    for bucket, leaves, P in zip(plan.reduce(), (lv["scene"], lv["human"], lv["refined"]), (Ps, Ph, Ph)):
+        _, views = _views_of(bucket, P)
+        for k, n in names.items():
+            ref = leaves[k].grad.reshape(P, -1)
+            assert torch.allclose(views[n], ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()) + 1e-12), (k, P)
+    assert float(lv["scene"]["mean_3d"].grad.abs().sum()) > 0 and float(lv["refined"]["rgb"].grad.abs().sum()) > 0
+
+
 def test_renderer_end_to_end_on_gpu(dev):
     from exavatar_release_b200 import GaussianRenderer
     from exavatar_release_b200.camera import look_at_cam_param
