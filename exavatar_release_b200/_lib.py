@@ -10,6 +10,7 @@ import os
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libb200raster.so")
+LIB_PATH = os.environ.get("B2R_LIB", LIB_PATH)  # tuning experiments: an alternative build of the same library
 
 B2R_OK = 0
 B2R_FLAG_NO_TILE_CULL = 1

@@ -24,7 +24,14 @@ namespace b2r {
 
 constexpr int B3_THREADS = 64;
 constexpr int B3_BATCH = 64;
-constexpr int B3_QUEUE = 16;  // queued splats per warp before phase B runs (two lanes share a splat)
+#ifndef B3_QUEUE_DEPTH
+#define B3_QUEUE_DEPTH 16
+#endif
+#ifndef B3_MIN_BLOCKS
+#define B3_MIN_BLOCKS 10  // 96 registers.  Measured on C2 / C4 (frames/s with 4 frames in flight; solo kernel us):
+#endif                    // depth 16 @ 96 regs 6737 / 105 (kept); 16 @ 80 regs 6728 / 105; 8 @ 72-80 regs 6400 / 121-127;
+                          // 32 @ 128 regs 6494 / 97 -- the deeper queue is faster alone but costs throughput in flight
+constexpr int B3_QUEUE = B3_QUEUE_DEPTH;  // queued splats per warp before phase B runs (32 / B3_QUEUE lanes share a splat)
 
 struct B3Stage {
   float4 a[B3_BATCH];  // px, py, A2, B2
@@ -45,7 +52,7 @@ __device__ __forceinline__ float rcp_approx(float x) {
 }
 
 template <bool HAS_DA>
-__global__ void __launch_bounds__(B3_THREADS) composite_bwd3_kernel(const B2RScene sc, const Ctx cx,
+__global__ void __launch_bounds__(B3_THREADS, B3_MIN_BLOCKS) composite_bwd3_kernel(const B2RScene sc, const Ctx cx,
                                                                     const B2RBackwardArgs args, float* __restrict__ gacc) {
   __shared__ B3Stage stage[2];
   __shared__ B3Compact compact[2];
@@ -104,30 +111,32 @@ __global__ void __launch_bounds__(B3_THREADS) composite_bwd3_kernel(const B2RSce
   const bool lane0 = lane == 0;
   const unsigned lanes_above = 0xfffffffeu << lane;  // lanes with a higher index (= later list entries)
 
-  // phase B: lanes l and l+16 share queued splat l, walk 16 pixels each and are combined with one shuffle per sum
+  // phase B: 32 / B3_QUEUE lanes share a queued splat, each walks its pixel rows; combined with shuffles
   auto drain = [&](const int count) {
-    constexpr int PIX = 16;
+    constexpr int SHARE = 32 / B3_QUEUE;  // lanes per queued splat
+    constexpr int ROWS = 4 / SHARE;       // pixel rows (of eight) per lane
+    static_assert(B3_QUEUE == 8 || B3_QUEUE == 16 || B3_QUEUE == 32, "queue depth");
     __syncwarp();
-    const int h = lane & (B3_QUEUE - 1), half = lane >> 4;
+    const int h = lane & (B3_QUEUE - 1), part = lane / B3_QUEUE;
     const bool live = h < count;
     float Sx = 0.f, Sy = 0.f, Sxx = 0.f, Sxy = 0.f, Syy = 0.f, Sq = 0.f, Sr = 0.f, Sg = 0.f, Sb = 0.f, Sd = 0.f;
     float4 m0 = make_float4(0.f, 0.f, 0.f, 0.f), m1 = make_float4(0.f, 1.f, 0.f, 0.f);
     if (live) {
       m0 = qm0[warp][h];
       m1 = qm1[warp][h];
-      // Two pixel rows of eight per lane.  Within a row dy is constant, so only q, q dx and q dx^2 are summed per
+      // ROWS pixel rows of eight per lane.  Within a row dy is constant, so only q, q dx and q dx^2 are summed per
       // pixel; the dy moments are formed once per row from the row sums.
       const float mx = m0.x - rx0, my = m0.y - ry0;
       float dxs[8];
 #pragma unroll
       for (int c = 0; c < 8; c++) dxs[c] = mx - (float)c;
 #pragma unroll
-      for (int r = 0; r < 2; r++) {
-        const float dy = my - (float)(half * 2 + r);
+      for (int r = 0; r < ROWS; r++) {
+        const float dy = my - (float)(part * ROWS + r);
         float Rq = 0.f, Rx = 0.f, Rxx = 0.f;
 #pragma unroll
         for (int c = 0; c < 8; c++) {
-          const int p = half * PIX + r * 8 + c;
+          const int p = (part * ROWS + r) * 8 + c;
           const float2 t = tb[warp][h][p];
           const float4 g = gpix[warp][p];
           const float hx = t.x * dxs[c];
@@ -148,17 +157,20 @@ __global__ void __launch_bounds__(B3_THREADS) composite_bwd3_kernel(const B2RSce
         Sxy = fmaf(Rx, dy, Sxy);
       }
     }
-    Sx += __shfl_xor_sync(0xffffffffu, Sx, 16);
-    Sy += __shfl_xor_sync(0xffffffffu, Sy, 16);
-    Sxx += __shfl_xor_sync(0xffffffffu, Sxx, 16);
-    Sxy += __shfl_xor_sync(0xffffffffu, Sxy, 16);
-    Syy += __shfl_xor_sync(0xffffffffu, Syy, 16);
-    Sq += __shfl_xor_sync(0xffffffffu, Sq, 16);
-    Sr += __shfl_xor_sync(0xffffffffu, Sr, 16);
-    Sg += __shfl_xor_sync(0xffffffffu, Sg, 16);
-    Sb += __shfl_xor_sync(0xffffffffu, Sb, 16);
-    if (HAS_DA) Sd += __shfl_xor_sync(0xffffffffu, Sd, 16);
-    if (live && half == 0) {
+#pragma unroll
+    for (int o = B3_QUEUE; o < 32; o <<= 1) {  // combine the lanes that share a splat
+      Sx += __shfl_xor_sync(0xffffffffu, Sx, o);
+      Sy += __shfl_xor_sync(0xffffffffu, Sy, o);
+      Sxx += __shfl_xor_sync(0xffffffffu, Sxx, o);
+      Sxy += __shfl_xor_sync(0xffffffffu, Sxy, o);
+      Syy += __shfl_xor_sync(0xffffffffu, Syy, o);
+      Sq += __shfl_xor_sync(0xffffffffu, Sq, o);
+      Sr += __shfl_xor_sync(0xffffffffu, Sr, o);
+      Sg += __shfl_xor_sync(0xffffffffu, Sg, o);
+      Sb += __shfl_xor_sync(0xffffffffu, Sb, o);
+      if (HAS_DA) Sd += __shfl_xor_sync(0xffffffffu, Sd, o);
+    }
+    if (live && part == 0) {
       // accumulator row convention of project_bwd.cu
       float* dst = gacc + (size_t)(__float_as_uint(m1.z) & 0x1fffffffu) * 12;
       red_add_v4(dst, 2.f * m0.z * Sx + m0.w * Sy, 2.f * m1.x * Sy + m0.w * Sx, Sxx, Sxy);
