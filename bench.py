@@ -155,21 +155,62 @@ def run_reference(args):
 # clocks
 # ---------------------------------------------------------------------------------------------------------------
 class ClockSampler:
+    """SM clock and throttle reasons sampled DURING the timed region.  The region lasts tens of milliseconds, far too
+    short for `nvidia-smi -lms`, so a thread polls NVML directly (~1 kHz); nvidia-smi is the fallback."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
+        import threading
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop = threading.Event()
+        self._thread = None
         self.proc, self.path = None, None
+        try:
+            import pynvml as N
+            N.nvmlInit()
+            h = N.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(N.nvmlDeviceGetMaxClockInfo(h, N.NVML_CLOCK_SM))
+            bits = {"hw_slowdown": getattr(N, "nvmlClocksThrottleReasonHwSlowdown", 0x8),
+                    "hw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40),
+                    "sw_thermal_slowdown": getattr(N, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20),
+                    "sw_power_cap": getattr(N, "nvmlClocksThrottleReasonSwPowerCap", 0x4)}
+
+            def poll():
+                while not self._stop.is_set():
+                    try:
+                        self.samples.append(float(N.nvmlDeviceGetClockInfo(h, N.NVML_CLOCK_SM)))
+                        r = int(N.nvmlDeviceGetCurrentClocksThrottleReasons(h))
+                        for name, bit in bits.items():
+                            if r & bit:
+                                self.reasons.add(name)
+                    except Exception:
+                        pass
+                    time.sleep(0.001)
+
+            self._thread = threading.Thread(target=poll, daemon=True)
+            self._thread.start()
+            return
+        except Exception:
+            self._thread = None
         exe = shutil.which("nvidia-smi")
         if exe is None:
             return
         fd, self.path = tempfile.mkstemp(suffix=".csv")
         os.close(fd)
         self.f = open(self.path, "w")
-        self.proc = subprocess.Popen([exe, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+        self.proc = subprocess.Popen([exe, f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20",
                                       "-i", str(index)], stdout=self.f, stderr=subprocess.DEVNULL)
 
     def stop(self):
+        if self._thread is not None:
+            self._stop.set()
+            self._thread.join(timeout=2)
+            if not self.samples:
+                return None
+            sm = sorted(self.samples)
+            return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                    "samples": len(sm), "source": "nvml, polled during the timed region"}
         if self.proc is None:
             return None
         self.proc.terminate()
@@ -193,7 +234,8 @@ class ClockSampler:
         if not sm:
             return None
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm),
+                "source": "nvidia-smi -lms 20"}
 
 
 # ---------------------------------------------------------------------------------------------------------------
