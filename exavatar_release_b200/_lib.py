@@ -27,6 +27,10 @@ class B2RScene(C.Structure):
         ("bg", _fp), ("viewmatrix", _fp), ("projmatrix", _fp), ("campos", _fp),
         ("means3D", _fp), ("shs", _fp), ("colors_precomp", _fp), ("opacities", _fp),
         ("scales", _fp), ("rotations", _fp), ("cov3D_precomp", _fp),
+        # fused linear-blend skinning; all NULL / 0 = off
+        ("skin_xyz", _fp), ("skin_weights", _fp), ("skin_joint_mats", _fp), ("skin_trans", _fp),
+        ("skin_cam_Rinv", _fp), ("skin_cam_t", _fp), ("skin_means_out", _fp), ("skin_J", C.c_int32),
+        ("skin_reserved", C.c_int32),
     ]
 
 
@@ -55,6 +59,7 @@ class B2RBackwardArgs(C.Structure):
         ("dL_dscales", _fp), ("dL_drotations", _fp), ("dL_dcov3D", _fp),
         ("flags", C.c_uint32), ("first_row", C.c_uint32),
         ("densify_grad_accum", _fp), ("densify_count", _fp), ("densify_radius_max", _fp),
+        ("dL_dskin_xyz", _fp), ("dL_dskin_G", _fp),
     ]
 
 
@@ -104,7 +109,7 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.b2r_abi_version() != 1:
+    if lib.b2r_abi_version() != 2:
         raise RuntimeError("b200raster: ABI version mismatch between the Python binding and libb200raster.so")
     for idx, cls in enumerate((B2RScene, B2RStatus, B2RWorkspace, B2RForwardOutputs, B2RBackwardArgs)):
         if lib.b2r_sizeof(idx) != C.sizeof(cls):

@@ -13,7 +13,14 @@ int validate_scene(const B2RScene* sc) {
   if (!(sc->tanfovx > 0.f) || !(sc->tanfovy > 0.f)) return B2R_E_INVALID;
   if (!sc->bg || !sc->viewmatrix || !sc->projmatrix || !sc->campos) return B2R_E_INVALID;
   if (sc->P > 0) {
-    if (!sc->means3D || !sc->opacities) return B2R_E_INVALID;
+    if (!sc->opacities) return B2R_E_INVALID;
+    if (sc->skin_xyz) {  // fused skinning replaces means3D
+      if (!sc->skin_weights || !sc->skin_joint_mats || !sc->skin_trans) return B2R_E_INVALID;
+      if (sc->skin_J <= 0 || sc->skin_J > 64) return B2R_E_INVALID;
+      if (sc->skin_cam_Rinv && !sc->skin_cam_t) return B2R_E_INVALID;
+    } else if (!sc->means3D) {
+      return B2R_E_INVALID;
+    }
     if ((sc->shs != nullptr) == (sc->colors_precomp != nullptr)) return B2R_E_INVALID;  // exactly one colour source
     const bool sr = sc->scales != nullptr && sc->rotations != nullptr;
     if (sr == (sc->cov3D_precomp != nullptr)) return B2R_E_INVALID;                      // exactly one covariance source

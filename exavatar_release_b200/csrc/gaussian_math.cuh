@@ -46,6 +46,46 @@ __device__ __forceinline__ float4 xform4x4(const float3 p, const float* m) {
                      m[2] * p.x + m[6] * p.y + m[10] * p.z + m[14], m[3] * p.x + m[7] * p.y + m[11] * p.z + m[15]);
 }
 
+// ---------------------------------------------------------------------------------------------------------------
+// Fused linear-blend skinning (avatar/common/nets/module.py:413-422, 555-557).
+//   M = sum_j w_j A_j (rows 0..2 of the 4x4),  posed = M [x,1] + trans,  world = Rinv (posed - t)
+// `wrow` is the Gaussian's weight row in the warp's shared-memory stage (stage_rows), `A` the (J,16) row-major joint
+// transforms in global memory (warp-uniform addresses: one broadcast line per load).
+// ---------------------------------------------------------------------------------------------------------------
+struct Skin {
+  float M[12];   // blended transform, rows 0..2, row-major 3x4
+  float3 x;      // canonical position
+  float3 world;  // posed position in the frame the rasteriser works in
+};
+
+__device__ __forceinline__ Skin skin_position(const B2RScene& sc, const int i, const float* __restrict__ wrow) {
+  Skin s;
+#pragma unroll
+  for (int k = 0; k < 12; k++) s.M[k] = 0.f;
+  const float* A = sc.skin_joint_mats;
+  for (int j = 0; j < sc.skin_J; j++) {
+    const float w = wrow[j];
+    if (w != 0.f) {  // SMPL-X skinning weights are sparse (a handful of joints per vertex)
+#pragma unroll
+      for (int k = 0; k < 12; k++) s.M[k] = fmaf(w, __ldg(A + 16 * j + k), s.M[k]);
+    }
+  }
+  s.x = make_float3(__ldg(sc.skin_xyz + 3 * (size_t)i), __ldg(sc.skin_xyz + 3 * (size_t)i + 1),
+                    __ldg(sc.skin_xyz + 3 * (size_t)i + 2));
+  float px = s.M[0] * s.x.x + s.M[1] * s.x.y + s.M[2] * s.x.z + s.M[3] + __ldg(sc.skin_trans);
+  float py = s.M[4] * s.x.x + s.M[5] * s.x.y + s.M[6] * s.x.z + s.M[7] + __ldg(sc.skin_trans + 1);
+  float pz = s.M[8] * s.x.x + s.M[9] * s.x.y + s.M[10] * s.x.z + s.M[11] + __ldg(sc.skin_trans + 2);
+  if (sc.skin_cam_Rinv) {
+    const float* R = sc.skin_cam_Rinv;
+    const float dx = px - __ldg(sc.skin_cam_t), dy = py - __ldg(sc.skin_cam_t + 1), dz = pz - __ldg(sc.skin_cam_t + 2);
+    px = __ldg(R) * dx + __ldg(R + 1) * dy + __ldg(R + 2) * dz;
+    py = __ldg(R + 3) * dx + __ldg(R + 4) * dy + __ldg(R + 5) * dz;
+    pz = __ldg(R + 6) * dx + __ldg(R + 7) * dy + __ldg(R + 8) * dz;
+  }
+  s.world = make_float3(px, py, pz);
+  return s;
+}
+
 // R_std of an un-normalised quaternion (r,x,y,z), row-major R[row*3+col]
 __device__ __forceinline__ void quat_to_R(const float4 q, float* R) {
   const float r = q.x, x = q.y, y = q.z, z = q.w;

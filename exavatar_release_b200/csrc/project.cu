@@ -70,6 +70,20 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
     __syncwarp();
     shrow = wstage + lane * S;
   }
+  // fused skinning: the warp's 32 weight rows (J floats each) take the same staged route as the SH rows
+  const float* wrow = nullptr;
+  if (sc.skin_xyz) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int J = sc.skin_J, S = J | 1;
+    float* base = reinterpret_cast<float*>(s_cnt + (aggregate ? cx.tiles : 0));
+    if (sc.shs) base += (size_t)8 * 32 * ((sc.sh_coeffs * 3) | 1);
+    float* wstage = base + (size_t)warp * 32 * S;
+    const int row0 = blockIdx.x * blockDim.x + warp * 32;
+    const int nrows = min(32, sc.P - row0);
+    if (nrows > 0) stage_rows<0>(wstage, const_cast<float*>(sc.skin_weights) + (size_t)row0 * J, J, nrows, 0xffffffffu);
+    __syncwarp();
+    wrow = wstage + lane * S;
+  }
   const Cam cam = load_cam(sc);
   bool visible = false;
   Geom g;
@@ -78,8 +92,18 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
   g.g2 = make_float4(0.f, 0.f, 0.f, 0.f);
   int4 aux = make_int4(0, 0, 0, 0);
   if (i < sc.P) {
-    const float3 p = make_float3(__ldg(sc.means3D + 3 * (size_t)i), __ldg(sc.means3D + 3 * (size_t)i + 1),
-                                 __ldg(sc.means3D + 3 * (size_t)i + 2));
+    float3 p;
+    if (wrow) {
+      p = skin_position(sc, i, wrow).world;
+      if (sc.skin_means_out) {
+        sc.skin_means_out[3 * (size_t)i] = p.x;
+        sc.skin_means_out[3 * (size_t)i + 1] = p.y;
+        sc.skin_means_out[3 * (size_t)i + 2] = p.z;
+      }
+    } else {
+      p = make_float3(__ldg(sc.means3D + 3 * (size_t)i), __ldg(sc.means3D + 3 * (size_t)i + 1),
+                      __ldg(sc.means3D + 3 * (size_t)i + 2));
+    }
     const float3 pv = xform4x3(p, cam.v);
     if (pv.z > K_NEAR) {  // App. A.1 step 1
       const float4 ph = xform4x4(p, cam.p);
@@ -274,10 +298,11 @@ int launch_project(const B2RScene& sc, const Ctx& cx, int32_t* radii, cudaStream
     ProfScope p(K_PROJECT, st);
     const int aggregate = cx.tiles <= 2048;  // beyond that the per-CTA sweeps over the tile table cost more than they save
     const size_t smem = (aggregate ? (size_t)cx.tiles * 4 : 0) +
-                        (sc.shs ? (size_t)8 * 32 * ((sc.sh_coeffs * 3) | 1) * sizeof(float) : 0);
+                        (sc.shs ? (size_t)8 * 32 * ((sc.sh_coeffs * 3) | 1) * sizeof(float) : 0) +
+                        (sc.skin_xyz ? (size_t)8 * 32 * (sc.skin_J | 1) * sizeof(float) : 0);
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 80 * 1024);
+      cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);
       attr_set = true;
     }
     launch_k(project_kernel, (sc.P + 255) / 256, 256, smem, st, true, sc, cx, radii, aggregate);

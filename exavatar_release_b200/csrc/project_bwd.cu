@@ -15,7 +15,8 @@ namespace b2r {
 // its SH gradient on exit (row layout k*3 + c, as in global memory); see the staging in the kernel below.
 __device__ __forceinline__ void project_bwd_one(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& out,
                                                 const float* __restrict__ gacc, const int i, const size_t oi,
-                                                const bool visible, const int4 aux, float* shrow) {
+                                                const bool visible, const int4 aux, float* shrow,
+                                                const float* wrow) {
   const int M = sc.sh_coeffs;
   const bool accumulate = (out.flags & B2R_BWD_ACCUMULATE) != 0;
 
@@ -25,6 +26,7 @@ __device__ __forceinline__ void project_bwd_one(const B2RScene& sc, const Ctx& c
   uint32_t clamp_bits = 0;
   float3 p = make_float3(0.f, 0.f, 0.f);
   Cam cam;
+  Skin skin;
 
   if (visible) {
     cam = load_cam(sc);
@@ -39,8 +41,13 @@ __device__ __forceinline__ void project_bwd_one(const B2RScene& sc, const Ctx& c
     dcol[0] = q2.x; dcol[1] = q2.y; dcol[2] = q2.z;
     clamp_bits = __float_as_uint(reinterpret_cast<const float4*>(cx.geom + i)[2].w) >> 29;
 
-    p = make_float3(__ldg(sc.means3D + 3 * (size_t)i), __ldg(sc.means3D + 3 * (size_t)i + 1),
-                    __ldg(sc.means3D + 3 * (size_t)i + 2));
+    if (wrow) {
+      skin = skin_position(sc, i, wrow);
+      p = skin.world;
+    } else {
+      p = make_float3(__ldg(sc.means3D + 3 * (size_t)i), __ldg(sc.means3D + 3 * (size_t)i + 1),
+                      __ldg(sc.means3D + 3 * (size_t)i + 2));
+    }
     float c6[6];
     float3 scl = make_float3(0.f, 0.f, 0.f);
     float4 q = make_float4(1.f, 0.f, 0.f, 0.f);
@@ -211,6 +218,32 @@ __device__ __forceinline__ void project_bwd_one(const B2RScene& sc, const Ctx& c
     if (accumulate) { d[0] += v[0]; d[1] += v[1]; d[2] += v[2]; }
     else { d[0] = v[0]; d[1] = v[1]; d[2] = v[2]; }
   };
+  // fused skinning: world-space gradient -> canonical position and the outer product the joint-transform GEMM needs
+  if (wrow && (out.dL_dskin_xyz || out.dL_dskin_G)) {
+    float gc[3] = {dm[0], dm[1], dm[2]}, dx[3] = {0.f, 0.f, 0.f}, G[12];
+    float xs[4] = {0.f, 0.f, 0.f, 0.f};
+    if (visible) {
+      if (sc.skin_cam_Rinv) {  // g_cam = Rinv^T g_world
+        const float* R = sc.skin_cam_Rinv;
+        gc[0] = __ldg(R) * dm[0] + __ldg(R + 3) * dm[1] + __ldg(R + 6) * dm[2];
+        gc[1] = __ldg(R + 1) * dm[0] + __ldg(R + 4) * dm[1] + __ldg(R + 7) * dm[2];
+        gc[2] = __ldg(R + 2) * dm[0] + __ldg(R + 5) * dm[1] + __ldg(R + 8) * dm[2];
+      }
+#pragma unroll
+      for (int c = 0; c < 3; c++) dx[c] = skin.M[c] * gc[0] + skin.M[4 + c] * gc[1] + skin.M[8 + c] * gc[2];
+      xs[0] = skin.x.x; xs[1] = skin.x.y; xs[2] = skin.x.z; xs[3] = 1.f;
+    }
+#pragma unroll
+    for (int r = 0; r < 3; r++)
+#pragma unroll
+      for (int c = 0; c < 4; c++) G[4 * r + c] = gc[r] * xs[c];
+    put3(out.dL_dskin_xyz, dx);
+    if (out.dL_dskin_G) {
+      float* d = out.dL_dskin_G + 12 * oi;
+#pragma unroll
+      for (int k = 0; k < 12; k++) { if (accumulate) d[k] += G[k]; else d[k] = G[k]; }
+    }
+  }
   const float dm2z[3] = {dm2[0], dm2[1], 0.f};
   put3(out.dL_dmeans3D, dm);
   put3(out.dL_dmeans2D, dm2z);
@@ -265,7 +298,15 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
     __syncwarp();
   }
   float* shrow = use_sh ? wstage + lane * S : nullptr;
-  if (active) project_bwd_one(sc, cx, out, gacc, i, (size_t)(i - first_row), visible, aux, shrow);
+  const float* wrow = nullptr;
+  if (sc.skin_xyz) {  // skinning weight rows, staged like the SH rows (after them in shared memory)
+    const int J = sc.skin_J, SJ = J | 1;
+    float* kstage = sh_stage + (use_sh ? (size_t)8 * 32 * S : 0) + (size_t)warp * 32 * SJ;
+    if (nrows > 0) stage_rows<0>(kstage, const_cast<float*>(sc.skin_weights) + (size_t)row0 * J, J, nrows, 0xffffffffu);
+    __syncwarp();
+    wrow = kstage + lane * SJ;
+  }
+  if (active) project_bwd_one(sc, cx, out, gacc, i, (size_t)(i - first_row), visible, aux, shrow, wrow);
   if (use_sh && nrows > 0) {
     const unsigned rows_active = __ballot_sync(0xffffffffu, active);
     __syncwarp();  // every lane's row is complete before the block is written out cooperatively
@@ -279,10 +320,11 @@ int launch_project_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs&
   ProfScope p(K_PROJECT_BWD, st, sc.P > 0 ? 1 : 0);
   if (sc.P > 0) {
     const bool use_sh = sc.shs != nullptr && a.dL_dshs != nullptr;
-    const size_t smem = use_sh ? (size_t)8 * 32 * ((sc.sh_coeffs * 3) | 1) * sizeof(float) : 0;
+    const size_t smem = (use_sh ? (size_t)8 * 32 * ((sc.sh_coeffs * 3) | 1) * sizeof(float) : 0) +
+                        (sc.skin_xyz ? (size_t)8 * 32 * (sc.skin_J | 1) * sizeof(float) : 0);
     static bool attr_set = false;
     if (!attr_set) {
-      cudaFuncSetAttribute(project_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024);
+      cudaFuncSetAttribute(project_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
       attr_set = true;
     }
     launch_k(project_bwd_kernel, (sc.P + 255) / 256, 256, smem, st, true, sc, cx, a, gacc);

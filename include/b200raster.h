@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B2R_ABI_VERSION 1
+#define B2R_ABI_VERSION 2
 
 #define B2R_OK 0
 #define B2R_E_INVALID (-1)      /* bad argument (null pointer, negative size, both / neither colour source ...) */
@@ -66,6 +66,22 @@ typedef struct B2RScene {
   const float* scales;        /* (P,3) or NULL */
   const float* rotations;     /* (P,4) (r,x,y,z), used un-normalised, or NULL */
   const float* cov3D_precomp; /* (P,6) or NULL  (exactly one of scales+rotations / cov3D_precomp) */
+  /* Optional fused linear-blend skinning in front of the projection.  ExAvatar poses its human
+   * Gaussians with  M_i = sum_j w_ij A_j,  posed_i = M_i [xyz_i, 1] + trans,  world_i = Rinv (posed_i - t)
+   * (avatar/common/nets/module.py:413-422 `get_transform_mat_vertex` / `lbs`, module.py:555-557) as five PyTorch
+   * kernels that write a (P,4,4) matrix per Gaussian.  With skin_xyz != NULL the projection kernels evaluate this per
+   * Gaussian in registers instead of reading `means3D` (which may then be NULL); the backward emits the gradient with
+   * respect to the canonical positions and the per-Gaussian outer products the joint-transform gradient is a GEMM of
+   * (B2RBackwardArgs.dL_dskin_xyz / dL_dskin_G). */
+  const float* skin_xyz;        /* (P,3) canonical ("big pose") positions, or NULL = no skinning */
+  const float* skin_weights;    /* (P,J) skinning weights of each Gaussian (rows already gathered, module.py:414) */
+  const float* skin_joint_mats; /* (J,16) row-major 4x4 transform per joint (module.py:385-411) */
+  const float* skin_trans;      /* (3) root translation added after blending (module.py:421) */
+  const float* skin_cam_Rinv;   /* (9) row-major inverse camera rotation, or NULL to stay in the posed frame */
+  const float* skin_cam_t;      /* (3) camera translation (used with skin_cam_Rinv) */
+  float* skin_means_out;        /* (P,3) optional OUTPUT: the posed world positions (other ExAvatar modules read them) */
+  int32_t skin_J;               /* joints (55 for SMPL-X); <= 64 */
+  int32_t skin_reserved;
 } B2RScene;
 
 /* Device-side status block; lives at offset 0 of the ctx buffer (read it back with a 64-byte D2H copy). */
@@ -126,6 +142,13 @@ typedef struct B2RBackwardArgs {
   float* densify_grad_accum;
   float* densify_count;
   float* densify_radius_max;
+  /* Fused skinning (B2RScene.skin_*), each may be NULL:
+   *   dL_dskin_xyz (P,3):  gradient w.r.t. the canonical positions,  (M_i[:3,:3])^T Rinv^T dL/dworld_i
+   *   dL_dskin_G   (P,12): row-major 3x4 outer product  (Rinv^T dL/dworld_i) [xyz_i, 1]^T ; the joint-transform gradient
+   *                        is the plain GEMM  dL/dA[:, :3, :] = W^T G  and  dL/dtrans = sum_i G_i[:, 3].
+   * Both follow `flags` (write / accumulate) and `first_row` like every other output. */
+  float* dL_dskin_xyz;
+  float* dL_dskin_G;
 } B2RBackwardArgs;
 #define B2R_BWD_ACCUMULATE 1u
 

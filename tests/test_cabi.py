@@ -31,7 +31,7 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_and_version():
     lib = L.load()
-    assert lib.b2r_abi_version() == 1
+    assert lib.b2r_abi_version() == 2
     for idx, cls in enumerate((L.B2RScene, L.B2RStatus, L.B2RWorkspace, L.B2RForwardOutputs, L.B2RBackwardArgs)):
         assert lib.b2r_sizeof(idx) == C.sizeof(cls)
     assert lib.b2r_sizeof(99) == 0
