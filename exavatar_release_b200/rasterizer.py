@@ -384,7 +384,7 @@ class _RasterizeSkinned(torch.autograd.Function):
         skin = {"xyz": _f32c(xyz, "xyz"), "weights": _f32c(skin_weights, "skin_weights"),
                 "joint_mats": _f32c(joint_mats, "joint_mats").reshape(-1, 16), "trans": _f32c(trans.reshape(3), "trans")}
         if cam_R is not None:
-            skin["Rinv"] = _f32c(torch.inverse(cam_R), "cam_R")
+            skin["Rinv"] = _f32c(_inv3(cam_R), "cam_R")
             skin["t"] = _f32c(cam_t.reshape(3), "cam_t")
         posed = torch.empty((P, 3), dtype=torch.float32, device=dev)
         color, radii, depth, alpha, cx = _forward_impl(raster_settings, posed, None, _f32c(colors_precomp, "colors_precomp"),
@@ -409,7 +409,7 @@ class _RasterizeSkinned(torch.autograd.Function):
         W = cx.keep["skin"]["weights"]
         J = W.shape[1]
         d_joint = torch.zeros((J, 4, 4), dtype=torch.float32, device=W.device)
-        d_joint[:, :3, :] = (W.t() @ d_G).view(J, 3, 4)  # the one dense contraction of this path: a plain library GEMM
+        d_joint[:, :3, :] = _tall_skinny_tn(W, d_G).view(J, 3, 4)  # the one dense contraction of this path: library GEMMs
         d_trans = d_G.view(-1, 3, 4)[:, :, 3].sum(0)
         return (d_xyz, None, d_joint.reshape(js), d_trans.reshape(ts), None, None, d_m2.reshape(m2s), d_col,
                 d_op.reshape(ops), d_sc, d_rot, None)
@@ -438,12 +438,39 @@ class SkinnedGaussianRasterizer(nn.Module):
                                        opacities, scales, rotations, self.raster_settings)
 
 
-def lbs_reference(xyz, skin_weights, joint_mats, trans, cam_R=None, cam_t=None):
-    """The unfused path, op for op as ExAvatar runs it (module.py:413-422, 555-557); device-agnostic, differentiable."""
+def _tall_skinny_tn(W: torch.Tensor, G: torch.Tensor, chunks: int = 64) -> torch.Tensor:
+    """W^T G for W (P,J), G (P,n) with P ~ 10^5 and J, n ~ 10: a batched GEMM over `chunks` row blocks plus a tiny sum.
+    A single (J x P)(P x n) GEMM leaves the library with one long-K tile and, depending on its heuristic, almost no
+    parallelism; the batched form always fills the machine."""
+    P, J = W.shape
+    n = G.shape[1]
+    pad = (-P) % chunks
+    if pad:
+        W = torch.cat((W, W.new_zeros(pad, J)))
+        G = torch.cat((G, G.new_zeros(pad, n)))
+    Wc = W.view(chunks, -1, J)
+    Gc = G.view(chunks, -1, n)
+    return torch.bmm(Wc.transpose(1, 2), Gc).sum(0)
+
+
+def _inv3(R: torch.Tensor) -> torch.Tensor:
+    """3x3 inverse by cofactors: a handful of elementwise kernels, no cuSOLVER call -- capturable in a CUDA graph
+    (`torch.inverse`, which the reference uses at module.py:556, synchronises)."""
+    a, b, c, d, e, f, g, h, i = R.reshape(9).unbind()
+    adj = torch.stack((e * i - f * h, c * h - b * i, b * f - c * e,
+                       f * g - d * i, a * i - c * g, c * d - a * f,
+                       d * h - e * g, b * g - a * h, a * e - b * d)).reshape(3, 3)
+    return adj / (a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g))
+
+
+def lbs_reference(xyz, skin_weights, joint_mats, trans, cam_R=None, cam_t=None, cam_R_inv=None):
+    """The unfused path, op for op as ExAvatar runs it (module.py:413-422, 555-557); device-agnostic, differentiable.
+    `cam_R_inv` (optional) skips the `torch.inverse` call, e.g. inside a CUDA-graph capture."""
     P, J = skin_weights.shape
     tmv = torch.matmul(skin_weights, joint_mats.reshape(J, 16)).view(P, 4, 4)
     xyz1 = torch.cat((xyz, torch.ones_like(xyz[:, :1])), 1)
     posed = torch.bmm(tmv, xyz1[:, :, None]).view(P, 4)[:, :3] + trans.reshape(1, 3)
-    if cam_R is not None:
-        posed = torch.matmul(torch.inverse(cam_R), (posed - cam_t.view(1, 3)).permute(1, 0)).permute(1, 0)
+    if cam_R is not None or cam_R_inv is not None:
+        Rinv = torch.inverse(cam_R) if cam_R_inv is None else cam_R_inv
+        posed = torch.matmul(Rinv, (posed - cam_t.view(1, 3)).permute(1, 0)).permute(1, 0)
     return posed

@@ -24,7 +24,7 @@ from exavatar_release_b200.synthetic import make_grad_image, make_population_ass
 def _rig(P, J, dtype, device, seed=5):
     g = torch.Generator().manual_seed(seed)
     w = torch.zeros(P, J)
-    idx = torch.stack([torch.randperm(J, generator=g)[:4] for _ in range(P)])
+    idx = torch.rand(P, J, generator=g).topk(4, dim=1).indices  # four distinct joints per Gaussian
     val = torch.rand(P, 4, generator=g) + 0.05
     w.scatter_(1, idx, val / val.sum(1, keepdim=True))  # four joints per Gaussian, weights sum to one
     ax = torch.randn(J, 3, generator=g)

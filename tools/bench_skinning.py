@@ -36,6 +36,7 @@ def main():
     w, A, trans = _rig(P, J, torch.float32, dev)
     xyz0 = human["mean_3d"] @ cam["R"].t() + cam["t"].view(1, 3)
     gi = make_grad_image(a.workload, 2).to(dev)
+    Rinv = torch.inverse(cam["R"])  # outside the timed / captured region for both paths
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     def leaves():
@@ -44,7 +45,7 @@ def main():
                 "opacity": human["opacity"].clone().requires_grad_()}
 
     def unfused(lv):
-        posed = RZ.lbs_reference(lv["xyz"], w, lv["A"], lv["trans"], cam["R"], cam["t"])
+        posed = RZ.lbs_reference(lv["xyz"], w, lv["A"], lv["trans"], None, cam["t"], cam_R_inv=Rinv)
         m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
         img = RZ.GaussianRasterizer(st)(means3D=posed, means2D=m2, opacities=lv["opacity"], colors_precomp=lv["rgb"],
                                         scales=lv["scale"], rotations=human["rotation"])[0]
@@ -62,28 +63,51 @@ def main():
                                   colors_precomp=human["rgb"], scales=human["scale"], rotations=human["rotation"])
     cap = int(RZ._state(dev).predicted[(P, W, H)] * 1.3) + 4096
     RZ.set_fixed_capacity(cap)
-    out = {}
+    out, out_graph = {}, {}
     for name, fn in (("unfused", unfused), ("fused", fused)):
         lv = leaves()
         for _ in range(5):
             fn(lv)
         torch.cuda.synchronize()
-        ms = 0.0
-        for _ in range(a.iters):
+
+        def timed(run):
+            ms = 0.0
+            for _ in range(a.iters):
+                flush.zero_()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                run()
+                e1.record()
+                torch.cuda.synchronize()
+                ms += e0.elapsed_time(e1)
+            return ms / a.iters
+
+        def eager():
             for v in lv.values():
                 v.grad = None
-            flush.zero_()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
             fn(lv)
-            e1.record()
-            torch.cuda.synchronize()
-            ms += e0.elapsed_time(e1)
-        out[name] = ms / a.iters
+
+        out[name] = timed(eager)
+        # the same work captured in a CUDA graph: removes the host cost of the extra PyTorch launches from the picture
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            eager()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize()
+        for v in lv.values():
+            v.grad = None
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            fn(lv)
+        g.replay()
+        torch.cuda.synchronize()
+        out_graph[name] = timed(g.replay)
     assert not RZ.overflowed()
-    print(f"{a.workload}: human population P={P}, J={J}, {W}x{H}; forward+backward through the public API, eager")
-    print(f"  unfused (5 PyTorch skinning ops + rasteriser): {out['unfused'] * 1e3:8.1f} us")
-    print(f"  fused   (SkinnedGaussianRasterizer)          : {out['fused'] * 1e3:8.1f} us   ({out['unfused'] / out['fused']:.2f}x)")
+    print(f"{a.workload}: human population P={P}, J={J}, {W}x{H}; forward+backward through the public API")
+    for tag, o in (("eager", out), ("CUDA graph", out_graph)):
+        print(f"  [{tag}] unfused (5 PyTorch skinning ops + rasteriser): {o['unfused'] * 1e3:8.1f} us")
+        print(f"  [{tag}] fused   (SkinnedGaussianRasterizer)          : {o['fused'] * 1e3:8.1f} us   ({o['unfused'] / o['fused']:.2f}x)")
 
 
 if __name__ == "__main__":
