@@ -64,6 +64,7 @@ class B2RBackwardArgs(C.Structure):
 
 
 B2R_BWD_ACCUMULATE = 1
+B2R_BWD_SCRATCH_ZEROED = 2
 
 
 # every symbol include/b200raster.h declares: (name, restype, argtypes)

@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(B2_THREADS) composite_bwd2_kernel(const B2RSce
 }
 
 int launch_composite_bwd2(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, float* gacc, cudaStream_t st) {
-  cudaMemsetAsync(gacc, 0, (size_t)(sc.P > 0 ? sc.P : 1) * 12 * sizeof(float), st);
+  if (!(a.flags & B2R_BWD_SCRATCH_ZEROED)) cudaMemsetAsync(gacc, 0, (size_t)(sc.P > 0 ? sc.P : 1) * 12 * sizeof(float), st);
   ProfScope p(K_COMPOSITE_BWD, st);
   if (a.dL_ddepth || a.dL_dalpha)
     launch_k(composite_bwd2_kernel<true>, cx.tiles * 4, B2_THREADS, 0, st, false, sc, cx, a, gacc);

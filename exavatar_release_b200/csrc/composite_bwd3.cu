@@ -295,7 +295,7 @@ int launch_composite_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArg
   // B2R_BWD_V2=1 selects the previous variant (composite_bwd2.cu) for A/B measurements
   static const bool use_v2 = getenv("B2R_BWD_V2") != nullptr;
   if (use_v2) return launch_composite_bwd2(sc, cx, a, gacc, st);
-  cudaMemsetAsync(gacc, 0, (size_t)(sc.P > 0 ? sc.P : 1) * 12 * sizeof(float), st);
+  if (!(a.flags & B2R_BWD_SCRATCH_ZEROED)) cudaMemsetAsync(gacc, 0, (size_t)(sc.P > 0 ? sc.P : 1) * 12 * sizeof(float), st);
   ProfScope p(K_COMPOSITE_BWD, st);
   if (a.dL_ddepth || a.dL_dalpha)
     launch_k(composite_bwd3_kernel<true>, cx.tiles * 4, B3_THREADS, 0, st, false, sc, cx, a, gacc);

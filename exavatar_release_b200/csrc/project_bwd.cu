@@ -307,6 +307,10 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
     wrow = kstage + lane * SJ;
   }
   if (active) project_bwd_one(sc, cx, out, gacc, i, (size_t)(i - first_row), visible, aux, shrow, wrow);
+  if ((out.flags & B2R_BWD_SCRATCH_ZEROED) && in_range && visible) {  // leave the accumulator clean for the next render
+    float4* row = reinterpret_cast<float4*>(const_cast<float*>(gacc)) + 3 * (size_t)i;
+    row[0] = row[1] = row[2] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
   if (use_sh && nrows > 0) {
     const unsigned rows_active = __ballot_sync(0xffffffffu, active);
     __syncwarp();  // every lane's row is complete before the block is written out cooperatively

@@ -37,7 +37,8 @@ class FramePlan:
         self.scratch_bytes = self.lib.b2r_scratch_bytes(P, width, height, self.capacity)
         self.scratch = torch.empty(self.scratch_bytes, dtype=torch.uint8, device=dev)
         self.bwd_bytes = self.lib.b2r_backward_scratch_bytes(P)
-        self.bwd_scratch = torch.empty(self.bwd_bytes, dtype=torch.uint8, device=dev)
+        # zero once: every backward leaves it zero again (B2R_BWD_SCRATCH_ZEROED), so no memset node per render
+        self.bwd_scratch = torch.zeros(self.bwd_bytes, dtype=torch.uint8, device=dev)
         self.ws = L.B2RWorkspace(self.ctx_buf.data_ptr(), self.ctx_bytes, self.ids.data_ptr(), self.capacity,
                                  self.scratch.data_ptr(), self.scratch_bytes, None, 0)
         self.out = L.B2RForwardOutputs(self.color.data_ptr(), self.depth.data_ptr(), self.alpha.data_ptr(),
@@ -71,7 +72,7 @@ class FramePlan:
         a = L.B2RBackwardArgs(_ptr(g_color), _ptr(g_depth), _ptr(g_alpha), _ptr(grads.get("means3D")),
                               _ptr(grads.get("means2D")), _ptr(grads.get("shs")), _ptr(grads.get("colors")),
                               _ptr(grads.get("opacities")), _ptr(grads.get("scales")), _ptr(grads.get("rotations")),
-                              _ptr(grads.get("cov3D")), L.B2R_BWD_ACCUMULATE if accumulate else 0, int(first_row),
+                              _ptr(grads.get("cov3D")), (L.B2R_BWD_ACCUMULATE if accumulate else 0) | L.B2R_BWD_SCRATCH_ZEROED, int(first_row),
                               _ptr((densify or {}).get("grad_accum")), _ptr((densify or {}).get("count")),
                               _ptr((densify or {}).get("radius_max")))
         with torch.cuda.device(self.device):

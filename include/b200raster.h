@@ -151,6 +151,10 @@ typedef struct B2RBackwardArgs {
   float* dL_dskin_G;
 } B2RBackwardArgs;
 #define B2R_BWD_ACCUMULATE 1u
+/* The caller guarantees `bwd_scratch` is all zero on entry; b2r_backward then skips its memset and leaves the scratch
+ * all zero again on return (the backward projection kernel clears each row after consuming it).  For callers that
+ * keep one scratch buffer alive across steps (plan.py): one graph node and one 48 B/Gaussian memset less per render. */
+#define B2R_BWD_SCRATCH_ZEROED 2u
 
 int b2r_abi_version(void);
 const char* b2r_strerror(int code);

@@ -539,6 +539,42 @@ def test_five_render_plan_matches_the_reference_pattern(dev):
     assert float(lv["scene"]["mean_3d"].grad.abs().sum()) > 0 and float(lv["refined"]["rgb"].grad.abs().sum()) > 0
 
 
+@pytest.mark.parametrize("deg,M", [(1, 4), (2, 9), (1, 16)])
+def test_sh_rows_of_any_width_are_staged_correctly(dev, deg, M):
+    """K1 / K6 move SH rows through shared memory; (P,16,3) takes the 128-bit path, every other coefficient count the
+    generic one.  GPU vs oracle for narrower rows, in write and in accumulate mode (two identical frames = 2x)."""
+    from exavatar_release_b200.plan import FramePlan, grad_bucket
+    rz = RZ()
+    wl = WORKLOADS["T2"]
+    a = make_assets("T2", seed=0)
+    shs = a["shs"][:, :M, :].contiguous()
+    st_c = workload_settings("T2", yaw=5.0)._replace(sh_degree=deg)
+    st_g = workload_settings("T2", yaw=5.0, device=dev, settings_cls=rz.GaussianRasterizationSettings)._replace(sh_degree=deg)
+    oc, orad, _, _, octx = O.forward(st_c, a["mean_3d"], a["opacity"], shs=shs, scales=a["scale"], rotations=a["rotation"])
+    gi = make_grad_image("T2", 0)
+    og = O.backward(octx, gi.numpy())
+    pm, gm = O.fragility(octx)
+    P = shs.shape[0]
+    assets = {k: v.to(dev) for k, v in a.items()}
+    assets["shs"] = shs.to(dev)
+    plan = FramePlan(P, wl.width, wl.height, 2_000_000, dev, sh_coeffs=M)
+    sc = plan.scene(0, st_g, assets)
+    flat, views = grad_bucket(P, dev, M)
+    for rep in range(2):
+        plan.forward(sc)
+        plan.backward(sc, gi.to(dev), views, accumulate=(rep > 0))
+        torch.cuda.synchronize()
+        assert np.array_equal(plan.radii.cpu().numpy(), orad)
+        _check("color", plan.color.cpu().numpy(), oc, np.broadcast_to(pm, oc.shape))
+        y = og["shs"] * (rep + 1)
+        row = np.broadcast_to(gm.reshape(-1, 1, 1), y.shape)
+        _check("d_shs", views["shs"].cpu().numpy(), y, row, max_bad_frac=0.2)
+        y3 = og["means3D"] * (rep + 1)
+        _check("d_means3D", views["means3D"].cpu().numpy(), y3, np.broadcast_to(gm[:, None], y3.shape), max_bad_frac=0.2)
+    if M > (deg + 1) ** 2:  # coefficients above the active degree receive exactly zero
+        assert float(views["shs"][:, (deg + 1) ** 2:, :].abs().max()) == 0.0
+
+
 def test_renderer_end_to_end_on_gpu(dev):
     from exavatar_release_b200 import GaussianRenderer
     from exavatar_release_b200.camera import look_at_cam_param
