@@ -12,14 +12,15 @@
 namespace b2r {
 
 int launch_priority(bool high) {
-  static int least = 0, greatest = 0;
-  static bool init = false;
-  if (!init) {
-    if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) least = greatest = 0;
-    if (getenv("B2R_NO_PRIORITY")) greatest = least;  // A/B switch for measurements
-    init = true;
-  }
-  return high ? greatest : least;
+  struct Range {
+    int least = 0, greatest = 0;
+    Range() {
+      if (cudaDeviceGetStreamPriorityRange(&least, &greatest) != cudaSuccess) least = greatest = 0;
+      if (getenv("B2R_NO_PRIORITY")) greatest = least;  // A/B switch for measurements
+    }
+  };
+  static const Range r;  // initialised once, thread-safely (forward and autograd-backward threads both launch)
+  return high ? r.greatest : r.least;
 }
 
 static std::atomic<int> g_prof_on{0};

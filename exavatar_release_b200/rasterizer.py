@@ -461,16 +461,3 @@ def _inv3(R: torch.Tensor) -> torch.Tensor:
                        f * g - d * i, a * i - c * g, c * d - a * f,
                        d * h - e * g, b * g - a * h, a * e - b * d)).reshape(3, 3)
     return adj / (a * (e * i - f * h) - b * (d * i - f * g) + c * (d * h - e * g))
-
-
-def lbs_reference(xyz, skin_weights, joint_mats, trans, cam_R=None, cam_t=None, cam_R_inv=None):
-    """The unfused path, op for op as ExAvatar runs it (module.py:413-422, 555-557); device-agnostic, differentiable.
-    `cam_R_inv` (optional) skips the `torch.inverse` call, e.g. inside a CUDA-graph capture."""
-    P, J = skin_weights.shape
-    tmv = torch.matmul(skin_weights, joint_mats.reshape(J, 16)).view(P, 4, 4)
-    xyz1 = torch.cat((xyz, torch.ones_like(xyz[:, :1])), 1)
-    posed = torch.bmm(tmv, xyz1[:, :, None]).view(P, 4)[:, :3] + trans.reshape(1, 3)
-    if cam_R is not None or cam_R_inv is not None:
-        Rinv = torch.inverse(cam_R) if cam_R_inv is None else cam_R_inv
-        posed = torch.matmul(Rinv, (posed - cam_t.view(1, 3)).permute(1, 0)).permute(1, 0)
-    return posed

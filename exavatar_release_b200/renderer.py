@@ -107,3 +107,18 @@ def scene_gaussian_assets(mean, opacity_logit, log_scale, rotation, feature_dc, 
         cam_pos = torch.matmul(torch.inverse(cam_param["R"]), -cam_param["t"].view(3, 1)).view(1, 3)
         assets["rgb"] = sh_to_rgb(int(active_sh_degree), sh, mean, cam_pos.to(mean.dtype))
     return assets
+
+
+def lbs_reference(xyz, skin_weights, joint_mats, trans, cam_R=None, cam_t=None, cam_R_inv=None):
+    """Caller-side mirror of how `HumanGaussian.forward` poses its Gaussians -- `get_transform_mat_vertex`, `lbs` and the
+    camera->world transform, op for op (module.py:413-422, 555-557); device-agnostic, differentiable.  This is the unfused
+    path `SkinnedGaussianRasterizer` is compared against; the product path never calls it.
+    `cam_R_inv` (optional) skips the `torch.inverse` call, e.g. inside a CUDA-graph capture."""
+    P, J = skin_weights.shape
+    tmv = torch.matmul(skin_weights, joint_mats.reshape(J, 16)).view(P, 4, 4)
+    xyz1 = torch.cat((xyz, torch.ones_like(xyz[:, :1])), 1)
+    posed = torch.bmm(tmv, xyz1[:, :, None]).view(P, 4)[:, :3] + trans.reshape(1, 3)
+    if cam_R is not None or cam_R_inv is not None:
+        Rinv = torch.inverse(cam_R) if cam_R_inv is None else cam_R_inv
+        posed = torch.matmul(Rinv, (posed - cam_t.view(1, 3)).permute(1, 0)).permute(1, 0)
+    return posed

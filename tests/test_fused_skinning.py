@@ -1,7 +1,7 @@
 """linear-blend skinning fused into the projection kernels.
 
 The unfused path is ExAvatar's own sequence of PyTorch ops (`get_transform_mat_vertex`, `lbs`, camera->world:
-avatar/common/nets/module.py:413-422, 555-557; restated op for op in `rasterizer.lbs_reference`) followed by the
+avatar/common/nets/module.py:413-422, 555-557; restated op for op in `renderer.lbs_reference`) followed by the
 rasteriser.  The fused path evaluates the same blend per Gaussian inside the projection kernels and returns gradients
 with respect to the canonical positions, the joint transforms and the root translation.  The two paths round the
 posed positions differently (a (P,55)x(55,16) GEMM vs. a sparse in-register blend), so discrete per-(pixel, splat)
@@ -16,7 +16,7 @@ import torch
 
 from util import workload_settings  # noqa: F401  (path setup)
 from exavatar_release_b200.camera import look_at_cam_param
-from exavatar_release_b200.rasterizer import lbs_reference
+from exavatar_release_b200.renderer import lbs_reference
 from exavatar_release_b200.renderer import render_settings
 from exavatar_release_b200.synthetic import make_grad_image, make_population_assets
 

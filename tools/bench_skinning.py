@@ -16,7 +16,7 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 
 from exavatar_release_b200 import rasterizer as RZ  # noqa: E402
 from exavatar_release_b200.camera import look_at_cam_param  # noqa: E402
-from exavatar_release_b200.renderer import render_settings  # noqa: E402
+from exavatar_release_b200.renderer import lbs_reference, render_settings  # noqa: E402
 from exavatar_release_b200.synthetic import WORKLOADS, make_grad_image, make_population_assets  # noqa: E402
 from test_fused_skinning import _rig  # noqa: E402
 
@@ -45,7 +45,7 @@ def main():
                 "opacity": human["opacity"].clone().requires_grad_()}
 
     def unfused(lv):
-        posed = RZ.lbs_reference(lv["xyz"], w, lv["A"], lv["trans"], None, cam["t"], cam_R_inv=Rinv)
+        posed = lbs_reference(lv["xyz"], w, lv["A"], lv["trans"], None, cam["t"], cam_R_inv=Rinv)
         m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
         img = RZ.GaussianRasterizer(st)(means3D=posed, means2D=m2, opacities=lv["opacity"], colors_precomp=lv["rgb"],
                                         scales=lv["scale"], rotations=human["rotation"])[0]
