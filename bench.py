@@ -1,22 +1,27 @@
 #!/usr/bin/env python
 """bench.py -- avatar train-step frames/s (forward + backward Gaussian rasterisation), BASELINE.json's metric.
 
-One "step" = every rank rasterises F frames of the workload (forward + backward, gradients of the frames summed
-into one per-rank bucket) followed, when N > 1, by ONE NCCL all-reduce of that bucket.
-Frames are independent, so ranks share nothing else: weak scaling.
+One "step" = every rank rasterises F frames of the workload (forward + backward; `--lanes` of them in flight on
+separate CUDA streams, gradients of the frames summed into one per-rank bucket) followed, when N > 1, by ONE NCCL
+all-reduce of that bucket.  Frames are independent, so ranks share nothing else: weak scaling.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--frames F] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--frames F] [--lanes S] [--impl b200|reference]
 
 Legs (all in one JSON line, printed by rank 0):
-  value     device-resident: inputs already in HBM, C ABI driven through FramePlan, the step captured in a CUDA graph
-  e2e       the public plugin API (GaussianRenderer -> GaussianRasterizer autograd) with HOST buffers: pinned H2D of
-            the Gaussian attributes + target image and D2H of loss + gradients inside the timed region
-  roofline  dominant kernel's algorithmic bytes / its live CUDA-event duration (in-library profiler, second pass)
-  cpu_baseline  the CPU oracle (oracle/, "port") timed on the host cores on a bounded sample of the same workload
+  value     device-resident: inputs already in HBM, C ABI driven through FrameLanes, the step captured in a CUDA graph
+  e2e       the public plugin API (GaussianRenderer -> GaussianRasterizer autograd, L1 loss, backward) with HOST buffers,
+            copies inside the timed region, the whole step in one CUDA graph.  --e2e-upload per-step (default): the
+            Gaussian parameter set goes host->device once per step (all frames of a step render it) plus one target
+            image per frame; the step's summed gradients and per-frame losses come back.  per-frame: every rasteriser
+            call uploads its full inputs and downloads its own gradients.
+  roofline  dominant kernel's algorithmic bytes / its live CUDA-event duration (in-library profiler, frames one at a time)
+  cpu_baseline  the CPU oracle (oracle/, "port") timed on the host cores on a bounded sample of the same workload (N = 1)
+  five_render   (--five-render) ExAvatar's five renders per training frame on FiveRenderPlan
 `--impl reference` times that CPU oracle through the same GaussianRenderer call as the reference arm.
 
 Timing: W >= 3 warm-up steps; L2 is flushed (256 MiB memset) before every timed step, outside the per-step CUDA
-event pairs; per-rank time = sum of per-step event durations; max over ranks.
+event pairs; per-rank time = sum of per-step event durations; max over ranks.  SM clocks / throttle reasons: NVML polled
+by a thread during the timed region.
 """
 from __future__ import annotations
 
@@ -676,7 +681,7 @@ def run_b200(args):
 
     # ---- leg 4: CPU baseline on the host cores (rank 0) ----
     cpu = None
-    if rank == 0 and not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only (the other ranks would idle)
         frame, threads = cpu_frame_fn(args.workload)
         frame(0)
         n, t0 = 0, time.perf_counter()
