@@ -132,36 +132,6 @@ __global__ void __launch_bounds__(256) scatter_agg_kernel(const B2RScene sc, con
                           });
 }
 
-// All-ascending bitonic network ("flip" then "disperse" steps).  Indices >= n behave as +inf keys, so no padding is
-// stored and n need not be a power of two.
-template <typename KeyPtr>
-__device__ __forceinline__ void bitonic_sort(KeyPtr key, const int n, const int npow2) {
-  const int half = npow2 >> 1;
-  for (int k = 2; k <= npow2; k <<= 1) {
-    const int hk = k >> 1;
-    for (int t = threadIdx.x; t < half; t += blockDim.x) {  // flip: i <-> block_end - offset
-      const int b = t / hk, off = t - b * hk;
-      const int i = b * k + off, j = b * k + k - 1 - off;
-      if (j < n) {
-        const unsigned long long a = key[i], c = key[j];
-        if (a > c) { key[i] = c; key[j] = a; }
-      }
-    }
-    __syncthreads();
-    for (int s = hk >> 1; s > 0; s >>= 1) {  // disperse: i <-> i + s
-      for (int t = threadIdx.x; t < half; t += blockDim.x) {
-        const int b = t / s, off = t - b * s;
-        const int i = 2 * s * b + off, j = i + s;
-        if (j < n) {
-          const unsigned long long a = key[i], c = key[j];
-          if (a > c) { key[i] = c; key[j] = a; }
-        }
-      }
-      __syncthreads();
-    }
-  }
-}
-
 // ---------------------------------------------------------------------------------------------------------------
 // K3: per-tile sort.  Order contract (App. A.2): ascending view depth, ties by ascending Gaussian index.
 //
@@ -173,7 +143,7 @@ __device__ __forceinline__ void bitonic_sort(KeyPtr key, const int n, const int 
 //     warp-private histogram (no atomics), one 256-digit scan, and a stable scatter;
 //   * ids are fetched once at the end; runs of bit-identical depths (rare: cloned Gaussians) are put in id order by
 //     an odd-even fix-up, which makes the result independent of the scatter's atomic arrival order.
-// Lists longer than CAP (16384) fall back to the in-place bitonic network in global memory.
+// Lists of >= 2048 entries are sorted in chunks of SORT_CHUNK and merged (merge_chunks_kernel): no length limit.
 // ---------------------------------------------------------------------------------------------------------------
 
 // Lanes holding the same 8-bit digit (invalid lanes match nobody).  Eight ballots instead of MATCH.ANY: on sm_100a
@@ -196,9 +166,10 @@ struct RadixSmem {
   static constexpr size_t bytes = (size_t)CAP * 12 + (size_t)W * 256 * 2 + 64;
 };
 
-template <int CAP, int THREADS>
-__device__ __forceinline__ void radix_sort_tile(const uint2* __restrict__ src, uint32_t* __restrict__ dst, const int n,
-                                                unsigned char* smem_raw) {
+// PAIRS = false: dst[i] = id of the i-th entry in (depth, id) order.  PAIRS = true (one chunk of a long list): the sorted
+// (depth, id) pairs are written back over the chunk itself, to be merged with the other chunks by merge_chunks_kernel.
+template <int CAP, int THREADS, bool PAIRS = false>
+__device__ __forceinline__ void radix_sort_tile(const uint2* src, uint32_t* dst, const int n, unsigned char* smem_raw) {
   constexpr int W = THREADS / 32;
   uint32_t* keyA = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* keyB = keyA + CAP;
@@ -327,7 +298,12 @@ __device__ __forceinline__ void radix_sort_tile(const uint2* __restrict__ src, u
     }
     if (!__syncthreads_or(changed)) break;
   }
-  for (int i = tid; i < n; i += THREADS) dst[i] = ids[i];
+  if (PAIRS) {
+    uint2* out = const_cast<uint2*>(src);  // every read of the chunk happened before the barriers above
+    for (int i = tid; i < n; i += THREADS) out[i] = make_uint2(kin[i], ids[i]);
+  } else {
+    for (int i = tid; i < n; i += THREADS) dst[i] = ids[i];
+  }
   __syncthreads();  // shared memory is reused by the next tile of this CTA
 }
 
@@ -445,77 +421,104 @@ __device__ __forceinline__ void warp_sort_tile(const uint2* __restrict__ src, ui
   __syncwarp();
 }
 
-// Large class: tiles with >= 2048 entries (the first n_large of tile_order), one CTA per SM, 201 KB of shared memory.
-template <int CAP, int THREADS>
-__global__ void __launch_bounds__(THREADS) sort_tiles_kernel(const Ctx cx) {
-  extern __shared__ __align__(16) unsigned char smem_raw[];
-  const int n_large = (int)(cx.status->reserved[0] & 0xffffffffull);
-  for (int t = blockIdx.x; t < n_large; t += gridDim.x) {
-    const uint2 r = cx.ranges[cx.tile_order[t]];  // longest lists first
-    const int n = (int)(r.y - r.x);
-    const uint2* src = cx.keys + r.x;
-    uint32_t* dst = cx.dup_ids + r.x;
-    if (n <= 0) continue;
-    if (n <= 32) {
-      if (threadIdx.x < 32) warp_sort_tile(src, dst, n, smem_raw);
-      __syncthreads();
-    } else if (n <= CAP) {
-      radix_sort_tile<CAP, THREADS>(src, dst, n, smem_raw);
-    } else {
-      // global fallback: keys are stored (depth_bits, id) = little-endian (lo, hi) words, so re-pack to depth-major first
-      unsigned long long* gk = reinterpret_cast<unsigned long long*>(cx.keys + r.x);
-      int npow2 = 2;
-      while (npow2 < n) npow2 <<= 1;
-      for (int i = threadIdx.x; i < n; i += blockDim.x) {
-        const uint2 kv = src[i];
-        gk[i] = ((unsigned long long)kv.x << 32) | kv.y;
-      }
-      __syncthreads();
-      bitonic_sort(gk, n, npow2);
-      for (int i = threadIdx.x; i < n; i += blockDim.x) dst[i] = (uint32_t)gk[i];
-      __syncthreads();
-    }
-  }
-}
-
-// One launch for every tile below SORT_SMALL entries.  tile_order is sorted by floor(log2 n) descending and the scan
-// kernel publishes how many tiles have n >= 2048 and n >= 512 (B2RStatus.reserved[0]), so CTA b knows its job without
-// searching: the first CTAs take one 512..2047-entry tile each (CTA-wide radix sort), the rest take eight shorter
-// tiles each, one per warp.  The grid is sized for the worst case; surplus CTAs exit at once.
+// One launch sorts every list.  tile_order is sorted by floor(log2 n) descending and the scan kernel publishes how many
+// tiles have n >= 2048 and n >= 512 plus a chunk table for the long ones (B2RStatus.reserved), so a CTA finds its work
+// items without searching.  Work items, heaviest first:
+//   1. one SORT_CHUNK-entry chunk of a list of >= 2048 entries: CTA-wide radix sort, sorted pairs written back in place
+//      (merged by merge_chunks_kernel);
+//   2. one list of 512..2047 entries: CTA-wide radix sort, ids written to their final place;
+//   3. eight lists shorter than 512 entries, one per warp.
+// The grid is the tile count; CTAs stride over the items and surplus CTAs exit at once.
 template <int CAP, int THREADS>
 __global__ void __launch_bounds__(THREADS) sort_mixed_kernel(const Ctx cx) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   B2R_TRACE_BEGIN();
   const unsigned long long cls = cx.status->reserved[0];
   const int n_large = (int)(cls & 0xffffffffull), n_ge512 = (int)(cls >> 32);
+  const int n_chunks = (int)cx.status->reserved[1];
   const int n_cta = n_ge512 - n_large;
-  const int b = blockIdx.x;
-  if (b < n_cta) {
-    const uint2 r = cx.ranges[cx.tile_order[n_large + b]];
-    const int n = (int)(r.y - r.x);  // < 2048; can be below 512 when the duplicate capacity clamped the range
-    const uint2* src = cx.keys + r.x;
-    uint32_t* dst = cx.dup_ids + r.x;
-    if (n > 32) {
-      radix_sort_tile<CAP, THREADS>(src, dst, n, smem_raw);
-    } else if (threadIdx.x < 32) {
-      warp_sort_tile(src, dst, n, smem_raw);
+  const int n_warp_items = (cx.tiles - n_ge512 + (THREADS / 32) - 1) / (THREADS / 32);
+  const int items = n_chunks + n_cta + n_warp_items;
+  int last_n = 0;
+  for (int b = blockIdx.x; b < items; b += gridDim.x) {
+    if (b < n_chunks) {
+      int lo = 0, hi = n_large - 1;  // the long list this chunk belongs to: last t with chunk_start[t] <= b
+      while (lo < hi) {
+        const int mid = (lo + hi + 1) >> 1;
+        if ((int)cx.chunk_start[mid] <= b) lo = mid; else hi = mid - 1;
+      }
+      const uint2 r = cx.ranges[cx.tile_order[lo]];
+      const int off = (b - (int)cx.chunk_start[lo]) * SORT_CHUNK;
+      const int len = min(SORT_CHUNK, (int)(r.y - r.x) - off);
+      if (len > 1) radix_sort_tile<CAP, THREADS, true>(cx.keys + r.x + off, nullptr, len, smem_raw);
+      last_n = len;
+    } else if (b < n_chunks + n_cta) {
+      const uint2 r = cx.ranges[cx.tile_order[n_large + (b - n_chunks)]];
+      const int n = (int)(r.y - r.x);  // < 2048; can be below 512 when the duplicate capacity clamped the range
+      const uint2* src = cx.keys + r.x;
+      uint32_t* dst = cx.dup_ids + r.x;
+      if (n > 32) {
+        radix_sort_tile<CAP, THREADS>(src, dst, n, smem_raw);
+      } else {
+        if (threadIdx.x < 32) warp_sort_tile(src, dst, n, smem_raw);
+        __syncthreads();
+      }
+      last_n = n;
+    } else {
+      const int warp = threadIdx.x >> 5;
+      const int t = n_ge512 + (b - n_chunks - n_cta) * (THREADS / 32) + warp;
+      if (t < cx.tiles) {
+        const uint2 r = cx.ranges[cx.tile_order[t]];
+        last_n = -(int)(r.y - r.x);
+        warp_sort_tile(cx.keys + r.x, cx.dup_ids + r.x, (int)(r.y - r.x), smem_raw + (size_t)warp * WSORT_BYTES);
+      }
     }
-    B2R_TRACE_END(n);
-    return;
   }
-  const int warp = threadIdx.x >> 5;
-  const int t = n_ge512 + (b - n_cta) * (THREADS / 32) + warp;
-  int n = 0;
-  if (t < cx.tiles) {
-    const uint2 r = cx.ranges[cx.tile_order[t]];
-    n = (int)(r.y - r.x);
-    warp_sort_tile(cx.keys + r.x, cx.dup_ids + r.x, n, smem_raw + (size_t)warp * WSORT_BYTES);
-  }
-  B2R_TRACE_END(-n);
+  B2R_TRACE_END(last_n);
 }
 
-constexpr int SORT_SMALL = 2048;   // 256 threads, 28 KB of shared memory: several CTAs per SM
-constexpr int SORT_LARGE = 16384;  // 512 threads, 201 KB of shared memory: one CTA per SM
+// Merge of the sorted chunks of the long lists: an entry's final position is its position in its own chunk plus, for
+// every other chunk of the list, the number of entries that precede it -- one binary search per other chunk on the
+// 64-bit (depth, id) key, which is unique, so the positions are a permutation.  Little shared state, so the kernel
+// co-resides with anything; it exits at once when no list is that long (the common case at ExAvatar's sizes).
+__global__ void __launch_bounds__(256) merge_chunks_kernel(const Ctx cx) {
+  const int n_large = (int)(cx.status->reserved[0] & 0xffffffffull);
+  const int n_chunks = (int)cx.status->reserved[1];
+  constexpr int SUB = SORT_CHUNK / 256;  // 256-entry work items per chunk
+  // flat work list (chunk, 256-entry block): every CTA gets the same amount of work however the lists are sized
+  for (int item = blockIdx.x; item < n_chunks * SUB; item += gridDim.x) {
+    const int b = item / SUB;
+    int lo = 0, hi = n_large - 1;  // the long list chunk b belongs to: last t with chunk_start[t] <= b
+    while (lo < hi) {
+      const int mid = (lo + hi + 1) >> 1;
+      if ((int)cx.chunk_start[mid] <= b) lo = mid; else hi = mid - 1;
+    }
+    const uint2 r = cx.ranges[cx.tile_order[lo]];
+    const int n = (int)(r.y - r.x);
+    const int c = b - (int)cx.chunk_start[lo];
+    const int e = c * SORT_CHUNK + (item - b * SUB) * 256 + (int)threadIdx.x;
+    if (e >= n || e >= (c + 1) * SORT_CHUNK) continue;
+    const uint2* pairs = cx.keys + r.x;
+    const int chunks = (n + SORT_CHUNK - 1) / SORT_CHUNK;
+    const uint2 me = pairs[e];
+    const unsigned long long key = ((unsigned long long)me.x << 32) | me.y;
+    int rank = e - c * SORT_CHUNK;
+    for (int c2 = 0; c2 < chunks; c2++) {
+      if (c2 == c) continue;
+      const uint2* q = pairs + c2 * SORT_CHUNK;
+      int l = 0, h = min(SORT_CHUNK, n - c2 * SORT_CHUNK);  // number of entries of chunk c2 below `key`
+      while (l < h) {
+        const int mid = (l + h) >> 1;
+        const uint2 v = q[mid];
+        if ((((unsigned long long)v.x << 32) | v.y) < key) l = mid + 1; else h = mid;
+      }
+      rank += l;
+    }
+    cx.dup_ids[r.x + rank] = me.y;
+  }
+}
+
+constexpr int SORT_SMALL = SORT_CHUNK;  // capacity of the CTA-wide sort = chunk size of the long lists
 
 int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t st) {
   // the two-phase entry re-derives ranges and cursors for the capacity the caller finally chose
@@ -542,21 +545,18 @@ int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t 
   constexpr int ST = 256;
   constexpr size_t cta_bytes = RadixSmem<SORT_SMALL, ST>::bytes, warp_bytes = (ST / 32) * WSORT_BYTES;
   constexpr size_t small_bytes = cta_bytes > warp_bytes ? cta_bytes : warp_bytes;
-  constexpr size_t large_bytes = RadixSmem<SORT_LARGE, 512>::bytes;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(sort_mixed_kernel<SORT_SMALL, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes);
-    cudaFuncSetAttribute(sort_tiles_kernel<SORT_LARGE, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)large_bytes);
     attr_set = true;
   }
   {
     ProfScope p(K_SORT_SMALL, st);
-    // worst case: every tile in the CTA class needs a CTA of its own (then there are no warp-class tiles left)
     launch_k(sort_mixed_kernel<SORT_SMALL, ST>, cx.tiles, ST, small_bytes, st, true, cx);
   }
   {
     ProfScope p(K_SORT_LARGE, st);
-    launch_k(sort_tiles_kernel<SORT_LARGE, 512>, cx.tiles < sms ? cx.tiles : sms, 512, large_bytes, st, true, cx);
+    launch_k(merge_chunks_kernel, 8 * sms, 256, 0, st, true, cx);
   }
   return check_launch();
 }

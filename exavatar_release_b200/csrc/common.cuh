@@ -25,6 +25,7 @@ constexpr float INV_LOG2E = 0.6931471805599453f;
 // that rounding in the per-pixel evaluation can never disagree with a cull decision
 constexpr float CULL_MARGIN2 = 0.02f;
 
+constexpr int SORT_CHUNK = 2048;  // per-tile sort: lists are sorted in chunks of this many entries (binning.cu)
 constexpr size_t ALIGN = 256;
 __host__ __device__ inline size_t align_up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
 
@@ -36,7 +37,7 @@ struct Geom {  // 48 bytes per Gaussian, three 16-byte vectors
 static_assert(sizeof(Geom) == 48, "Geom must be 48 bytes");
 
 struct CtxLayout {
-  size_t status, geom, aux, ranges, tile_count, tile_cursor, tile_order, final_T, n_contrib, total;
+  size_t status, geom, aux, ranges, tile_count, tile_cursor, tile_order, chunk_start, final_T, n_contrib, total;
   int gx, gy, tiles;
 };
 __host__ __device__ inline CtxLayout ctx_layout(int P, int W, int H) {
@@ -53,6 +54,7 @@ __host__ __device__ inline CtxLayout ctx_layout(int P, int W, int H) {
   L.tile_count = o; o += align_up((size_t)L.tiles * 4);
   L.tile_cursor = o; o += align_up((size_t)L.tiles * 4);
   L.tile_order = o; o += align_up((size_t)L.tiles * 4);
+  L.chunk_start = o; o += align_up((size_t)L.tiles * 4);
   L.final_T = o; o += align_up(N * 4);
   L.n_contrib = o; o += align_up(N * 4);
   L.total = o;
@@ -84,6 +86,7 @@ struct Ctx {
   uint32_t* tile_count;
   uint32_t* tile_cursor;
   uint32_t* tile_order;  // tiles sorted longest list first (see tile_scan_kernel)
+  uint32_t* chunk_start; // first sort chunk of the t-th tile of tile_order, for the tiles of >= 2048 entries
   uint2* keys;
   uint64_t* status_mirror;
   uint64_t status_token;
@@ -107,6 +110,7 @@ inline Ctx resolve(const B2RWorkspace* ws, int P, int W, int H) {
   x.tile_count = (uint32_t*)(c + L.tile_count);
   x.tile_cursor = (uint32_t*)(c + L.tile_cursor);
   x.tile_order = (uint32_t*)(c + L.tile_order);
+  x.chunk_start = (uint32_t*)(c + L.chunk_start);
   x.keys = s ? (uint2*)(s + S.keys) : nullptr;
   x.status_mirror = ws->status_mirror;
   x.status_token = ws->status_token;

@@ -101,7 +101,7 @@ int b2r_profile_read(double* ms_sum, uint64_t* counts, int reset) {
 uint64_t b2r_launch_count(void) { return g_launches.load(); }
 
 const char* b2r_kernel_name(int id) {
-  static const char* names[B2R_NUM_KERNELS] = {"project", "tile_scan", "scatter", "sort_small", "sort_large",
+  static const char* names[B2R_NUM_KERNELS] = {"project", "tile_scan", "scatter", "sort_small", "sort_merge",
                                                "composite_fwd", "composite_bwd", "project_bwd", "misc"};
   return (id >= 0 && id < B2R_NUM_KERNELS) ? names[id] : "?";
 }

@@ -234,6 +234,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx) {
   // by floor(log2(n)) descending.  Tile cost is ~linear in n and spans three orders of magnitude, so launching in
   // index order leaves most SMs idle behind a few heavy tiles that happened to start late.
   __shared__ uint32_t bin_cursor[34];
+  __shared__ uint32_t n_large_s;
   if (threadIdx.x < 34) bin_cursor[threadIdx.x] = 0;
   __syncthreads();
   auto bin_of = [](uint32_t n) { return n == 0 ? 33 : __clz(n); };  // clz = 31 - floor(log2 n): small bin = long list
@@ -248,11 +249,36 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx) {
     }
     // class boundaries of the per-tile sort (binning.cu): bins 0..20 hold n >= 2048, bins 0..22 hold n >= 512
     cx.status->reserved[0] = (unsigned long long)bin_cursor[21] | ((unsigned long long)bin_cursor[23] << 32);
+    n_large_s = bin_cursor[21];
   }
   __syncthreads();
   for (int t = threadIdx.x; t < cx.tiles; t += blockDim.x) {
     const uint32_t pos = atomicAdd(&bin_cursor[bin_of(cx.tile_count[t])], 1u);
     cx.tile_order[pos] = (uint32_t)t;
+  }
+  __syncthreads();
+  // Tiles of >= 2048 entries are sorted in chunks of SORT_CHUNK by separate CTAs and merged afterwards (binning.cu):
+  // chunk_start[t] = first chunk of the t-th tile of tile_order, reserved[1] = number of chunks.
+  if (warp == 0) {
+    const uint32_t n_large = n_large_s;
+    uint32_t run = 0;
+    for (uint32_t base = 0; base < n_large; base += 32) {
+      const uint32_t t = base + lane;
+      uint32_t c = 0;
+      if (t < n_large) {
+        const uint2 r = cx.ranges[cx.tile_order[t]];
+        c = (r.y - r.x + SORT_CHUNK - 1) / SORT_CHUNK;
+      }
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      if (t < n_large) cx.chunk_start[t] = run + incl - c;
+      run += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) cx.status->reserved[1] = run;
   }
   if (threadIdx.x == 0) {
     const uint64_t total = carry_s;
