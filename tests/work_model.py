@@ -58,7 +58,10 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--workload", default="C2")
     ap.add_argument("--yaw", type=float, default=5.0)
+    ap.add_argument("--rect", default="8x4", help="pixel rect one cull test / hit covers (WxH), to compare decompositions: "
+                                                    "8x4 is what the kernels use (one warp = one rect)")
     a = ap.parse_args()
+    RW, RH = (int(v) for v in a.rect.split("x"))
     wl = WORKLOADS[a.workload]
     H, W = wl.height, wl.width
     assets = make_assets(a.workload, seed=0)
@@ -95,12 +98,12 @@ def main():
         tot["kept"] += int(keep.sum())
         g, pos = g[keep], pos[keep]
         tile_hits = 0
-        for wy in range(4):          # 8 warps per tile: 2 columns x 4 rows of 8x4 pixel rects
-            for wx in range(2):
-                rx0, ry0 = x0 + 8 * wx, y0 + 4 * wy
+        for wy in range(16 // RH):   # 8x4: 8 warps per tile, 2 columns x 4 rows of pixel rects
+            for wx in range(16 // RW):
+                rx0, ry0 = x0 + RW * wx, y0 + RH * wy
                 if rx0 >= W or ry0 >= H:
                     continue
-                rx1, ry1 = min(rx0 + 7, W - 1), min(ry0 + 3, H - 1)
+                rx1, ry1 = min(rx0 + RW - 1, W - 1), min(ry0 + RH - 1, H - 1)
                 px = np.arange(int(rx0), int(rx1) + 1)
                 py = np.arange(int(ry0), int(ry1) + 1)
                 nc = ncon[np.ix_(py, px)]                       # (rows, cols) contributors per pixel
@@ -131,15 +134,19 @@ def main():
         longest.append((tile_hits, n, t))
     longest.sort(reverse=True)
     f = tot
-    print(f"{a.workload} yaw {a.yaw}: P={len(radii)}, visible={(radii > 0).sum()}, {gx * gy} tiles")
+    print(f"{a.workload} yaw {a.yaw}: P={len(radii)}, visible={(radii > 0).sum()}, {gx * gy} tiles, rect {RW}x{RH}")
+    LANES = RW * RH
     print(f"  list entries (3-sigma rects)        {f['entries']:>10d}")
     print(f"  kept by the exact tile cull         {f['kept']:>10d}  ({100 * f['kept'] / f['entries']:.1f} %)")
     for tag, name, ipt in (("f", "forward", 31.0), ("b", "backward", 48.5 + 12.5)):
         wt, wh, us = f["warp_tests_" + tag], f["warp_hits_" + tag], f["useful_" + tag]
         inst = wh * ipt + wt / 32.0 * 45.0
         cyc = inst / (148 * 4)
-        print(f"  {name}: warp tests {wt:>9d}  warp hits {wh:>9d} ({100 * wh / max(wt, 1):.1f} %)  lane evaluations {32 * wh:>10d}"
-              f"  useful {us:>10d} ({100 * us / max(32 * wh, 1):.1f} % of the lanes)")
+        print(f"  {name}: rect tests {wt:>9d}  rect hits {wh:>9d} ({100 * wh / max(wt, 1):.1f} %)  lane evaluations {LANES * wh:>10d}"
+              f"  useful {us:>10d} ({100 * us / max(LANES * wh, 1):.1f} % of the lanes)")
+        if LANES != 32:
+            print(f"      (a {RW}x{RH} rect is {LANES} lanes: {LANES * wh / 32:.0f} warp-hit equivalents)")
+            continue
         print(f"      modelled warp-instructions {inst / 1e6:6.1f} M  ->  {cyc / 1.965e3:6.1f} us at one instruction per scheduler per cycle"
               f" (148 SMs x 4, 1.965 GHz); useful lane-evaluations at the same rate would need"
               f" {us / 32 * ipt / (148 * 4) / 1.965e3:5.1f} us")
