@@ -107,3 +107,16 @@ def test_fused_skinning_matches_the_unfused_path(world):
         _close(k, b[k].grad, a[k].grad)
     _close("means2D", m2b.grad, m2a.grad)
     assert float(a["A"].grad[:, 3, :].abs().max()) == 0.0 and float(b["A"].grad[:, 3, :].abs().max()) == 0.0
+
+
+def test_host_helpers_of_the_skinning_backward():
+    """`_inv3` (graph-capturable 3x3 inverse) and `_tall_skinny_tn` (W^T G as a batched GEMM) against the plain ops."""
+    from exavatar_release_b200.rasterizer import _inv3, _tall_skinny_tn
+    g = torch.Generator().manual_seed(11)
+    for _ in range(5):
+        R = torch.randn(3, 3, generator=g, dtype=torch.float64) + 2 * torch.eye(3, dtype=torch.float64)
+        assert torch.allclose(_inv3(R), torch.inverse(R), rtol=1e-10, atol=1e-12)
+    for P, J, n, chunks in ((1000, 55, 12, 64), (1001, 7, 3, 8), (5, 4, 2, 64)):
+        W = torch.rand(P, J, generator=g, dtype=torch.float64)
+        G = torch.randn(P, n, generator=g, dtype=torch.float64)
+        assert torch.allclose(_tall_skinny_tn(W, G, chunks), W.t() @ G, rtol=1e-10, atol=1e-10)
