@@ -229,9 +229,7 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ wstage, float* __
 #pragma unroll
       for (int u = 0; u < 12; u++) {
         const int j = lane + 32 * u;
-        // masked rows are never touched, not even read: with a detached prefix they lie before the output buffer
-        const bool rd = j < n4 && (MODE == 0 || ((row_mask >> (j / 12)) & 1u));
-        v[u] = rd ? (MODE == 0 ? __ldg(g4 + j) : g4[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[u] = j < n4 ? (MODE == 0 ? __ldg(g4 + j) : g4[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 #pragma unroll
@@ -257,7 +255,7 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ wstage, float* __
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         const int e = e0 + 32 * u;
-        v[u] = (e < total && (MODE == 0 || ((row_mask >> (e / L)) & 1u))) ? gptr[e] : 0.f;
+        v[u] = e < total ? gptr[e] : 0.f;
       }
     }
 #pragma unroll
