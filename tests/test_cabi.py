@@ -86,3 +86,62 @@ def test_kernel_names():
     names = [lib.b2r_kernel_name(i).decode() for i in range(9)]
     assert names[0] == "project" and names[5] == "composite_fwd" and names[6] == "composite_bwd"
     assert lib.b2r_kernel_name(99) == b"?"
+
+
+def test_error_codes_of_the_round1_additions_without_touching_cuda():
+    """Validation of the fields added in ABI v2 (fused skinning, detached prefix, SH row limit, id width) happens on the
+    host before any launch, so it is testable without a GPU."""
+    lib = L.load()
+    fake = 0x1000
+    sc = L.B2RScene()
+    sc.P, sc.width, sc.height, sc.tanfovx, sc.tanfovy = 10, 32, 32, 0.5, 0.5
+    sc.bg = sc.viewmatrix = sc.projmatrix = sc.campos = fake
+    sc.opacities = sc.colors_precomp = sc.scales = sc.rotations = fake
+    ws = L.B2RWorkspace()
+    ws.ctx, ws.ctx_bytes = fake, 16  # too small on purpose: a scene that validates reaches the workspace check (-2)
+    out = L.B2RForwardOutputs()
+    fwd = lambda: lib.b2r_forward(C.byref(sc), C.byref(ws), C.byref(out), None)
+    assert fwd() == -1                      # neither means3D nor skinning
+    sc.means3D = fake
+    assert fwd() == -2
+    # fused skinning replaces means3D, but needs all of its inputs and a sane joint count
+    sc.means3D = None
+    sc.skin_xyz = fake
+    assert fwd() == -1
+    sc.skin_weights = sc.skin_joint_mats = sc.skin_trans = fake
+    sc.skin_J = 0
+    assert fwd() == -1
+    sc.skin_J = 65
+    assert fwd() == -1
+    sc.skin_J = 55
+    assert fwd() == -2
+    sc.skin_cam_Rinv = fake                 # camera rotation without its translation
+    assert fwd() == -1
+    sc.skin_cam_t = fake
+    assert fwd() == -2
+    # SH rows are staged through shared memory: at most 16 coefficients, degree <= 3, enough coefficients for the degree
+    sc.colors_precomp = None
+    sc.shs = fake
+    sc.sh_degree, sc.sh_coeffs = 3, 16
+    assert fwd() == -2
+    sc.sh_coeffs = 9
+    assert fwd() == -1
+    sc.sh_degree, sc.sh_coeffs = 1, 17
+    assert fwd() == -1
+    sc.sh_degree, sc.sh_coeffs = 4, 25
+    assert fwd() == -1
+    sc.shs, sc.colors_precomp, sc.sh_degree, sc.sh_coeffs = None, fake, 0, 0
+    # the splat record carries the Gaussian id in 29 bits
+    sc.P = 1 << 29
+    assert fwd() == -1
+    sc.P = 10
+    # backward: colour gradient and scratch are mandatory, the detached prefix cannot exceed P
+    args = L.B2RBackwardArgs()
+    ws.ctx_bytes = lib.b2r_ctx_bytes(10, 32, 32)
+    bwd = lambda scratch, nbytes: lib.b2r_backward(C.byref(sc), C.byref(ws), C.byref(args), scratch, nbytes, None)
+    assert bwd(fake, 1 << 20) == -1         # no dL_dcolor
+    args.dL_dcolor = fake
+    assert bwd(None, 1 << 20) == -1
+    assert bwd(fake, 8) == -2               # scratch too small
+    args.first_row = 11
+    assert bwd(fake, 1 << 20) == -1
