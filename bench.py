@@ -1,31 +1,39 @@
 #!/usr/bin/env python
 """bench.py -- avatar train-step frames/s (forward + backward Gaussian rasterisation), BASELINE.json's metric.
 
-One "step" = every rank rasterises F frames of the workload (forward + backward; `--lanes` of them in flight on
-separate CUDA streams, gradients of the frames summed into one per-rank bucket) followed, when N > 1, by ONE NCCL
-all-reduce of that bucket.  Frames are independent, so ranks share nothing else: weak scaling.
+Default workload: BASELINE.json configs[3] = **C4, the NeuMan-style training frame**: 167 k human + 130 k scene Gaussians
+at 512x512, rendered the way ExAvatar trains (avatar/main/model.py:81-162): FIVE rasteriser calls per frame -- scene |
+human (random bg) | cat(scene.detach(), human) | human_refined | cat(scene.detach(), human_refined) -- each forward +
+backward.  One "step" = every rank runs F such training frames (default 8) and, when N > 1, ONE NCCL all-reduce of the
+flat gradient bucket plus the small densification-statistics all-reduce.  `value` = training
+frames/s of the whole job (a frame = 5 renders).  `--pattern single` (and every workload without both populations: C1,
+C3, C5) times one render per frame instead, as round 1 did; the C2 single-render number stays in the line as
+`single_render`.
 
-  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C2] [--frames F] [--lanes S] [--impl b200|reference]
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--workload C4] [--pattern auto|five|single] [--frames F]
+                  [--lanes S] [--impl b200|reference]
 
-Legs (all in one JSON line, printed by rank 0):
-  value     device-resident: inputs already in HBM, C ABI driven through FrameLanes, the step captured in a CUDA graph
-  e2e       the public plugin API (GaussianRenderer -> GaussianRasterizer autograd, L1 loss, backward) with HOST buffers,
-            copies inside the timed region, the whole step in one CUDA graph.  --e2e-upload per-step (default): the
-            Gaussian parameter set goes host->device once per step (all frames of a step render it) plus one target
-            image per frame; the step's summed gradients and per-frame losses come back.  per-frame: every rasteriser
-            call uploads its full inputs and downloads its own gradients.
-  roofline  dominant kernel's algorithmic bytes / its live CUDA-event duration (in-library profiler, frames one at a time)
-  cpu_baseline  the CPU oracle (oracle/, "port") timed on the host cores on a bounded sample of the same workload (N = 1)
-  five_render   (--five-render) ExAvatar's five renders per training frame on FiveRenderPlan
-`--impl reference` times that CPU oracle through the same GaussianRenderer call as the reference arm.
+Legs (one JSON line, rank 0):
+  value        device-resident: inputs in HBM, C ABI driven through the plan objects, the step captured in a CUDA graph
+  e2e          the public plugin API (GaussianRenderer -> GaussianRasterizer autograd, L1 loss, backward) with pinned HOST
+               buffers; host->device: the Gaussian parameter sets once per step + one target image per frame; device->host:
+               the step's summed gradients + per-frame losses; the whole step in one CUDA graph (fixed-capacity mode)
+  e2e_eager    same API with the UNMODIFIED reference call shape (GaussianRenderer.forward(assets, shape, cam, bg): camera
+               matrices rebuilt per call, adaptive capacity, no graph) -- what a user who only swaps the import gets
+  roofline     dominant kernel's algorithmic bytes / its live CUDA-event duration (in-library profiler, renders one at a
+               time); per-kernel table
+  strong_scaling (N > 1) BASELINE configs[3] literally: a global batch of 8 frames sharded over the ranks (rank r takes
+               frames r::N), loss pre-divided by the global batch (train.py:43), same collectives
+  cpu_baseline the CPU oracle (oracle/, kind "port") on the host cores, bounded sample of the same pattern (N = 1 only)
+`--impl reference` times that CPU oracle on the same pattern through the same GaussianRenderer call (reference arm).
 
-Timing: W >= 3 warm-up steps; L2 is flushed (256 MiB memset) before every timed step, outside the per-step CUDA
-event pairs; per-rank time = sum of per-step event durations; max over ranks.  SM clocks / throttle reasons: NVML polled
-by a thread during the timed region.
+Timing: W >= 3 warm-up steps; L2 flushed (256 MiB memset) before every timed step, outside the per-step CUDA event pairs;
+per-rank time = sum of per-step event durations; max over ranks.  Clocks: NVML polled by a thread during the timed region.
 """
 from __future__ import annotations
 
 import argparse
+import ctypes as C
 import json
 import os
 import shutil
@@ -40,10 +48,12 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 from exavatar_release_b200.camera import look_at_cam_param  # noqa: E402
-from exavatar_release_b200.synthetic import WORKLOADS, make_assets, make_grad_image  # noqa: E402
+from exavatar_release_b200.synthetic import WORKLOADS, make_assets, make_grad_image, make_population_assets  # noqa: E402
 
 METRIC = "avatar train-step frames/sec (fwd+bwd raster)"
 UNIT = "frames/s"
+FIVE = ("scene", "human", "scene_human", "human_refined", "scene_human_refined")
+BG_RAND = (0.3, 0.7, 0.2)  # stands for model.py:72 `bg = torch.rand(3)` (fixed so runs are comparable)
 
 
 def parse():
@@ -52,19 +62,21 @@ def parse():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="C2", choices=[k for k in WORKLOADS if k.startswith("C")])
+    ap.add_argument("--workload", default="C4", choices=[k for k in WORKLOADS if k.startswith("C")])
+    ap.add_argument("--pattern", default="auto", choices=["auto", "five", "single"],
+                    help="five: ExAvatar's five renders per training frame (needs both populations); single: one render")
     ap.add_argument("--frames", type=int, default=8, help="frames per rank per step")
-    ap.add_argument("--lanes", type=int, default=4, help="frames in flight per rank (CUDA streams; 1 = serial)")
+    ap.add_argument("--lanes", type=int, default=4, help="single pattern: frames in flight per rank (CUDA streams)")
+    ap.add_argument("--engine", default=os.environ.get("B2R_FIVE_ENGINE", "merged"), choices=["merged", "separate"],
+                    help="five pattern: merged = two projection/binning passes shared by the five renders (SURVEY 8f-3); "
+                         "separate = five independent renders on five streams (round-1 FiveRenderPlan)")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-eager", action="store_true", help="skip the e2e_eager leg")
+    ap.add_argument("--no-single", action="store_true", help="five pattern: skip the extra C2 single-render key")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--e2e-upload", default="per-step", choices=["per-step", "per-frame"],
-                    help="e2e leg: copy the Gaussian set host->device once per step (the frames of a step share it, as in "
-                         "the device-resident leg; result = losses + the step's summed gradients) or once per frame "
-                         "(every rasteriser call gets fresh host inputs and returns its own gradients)")
-    ap.add_argument("--five-render", action="store_true",
-                    help="extra leg: ExAvatar's five-render training frame (model.py:81-162) on FiveRenderPlan; needs a "
-                         "workload with both populations (C2, C4)")
+                    help="single pattern e2e: Gaussian set host->device once per step or once per frame")
     ap.add_argument("--trace-e2e", default=None, help="write a chrome trace (CUPTI via torch.profiler) of one e2e step here")
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="CPU budget of the cpu_baseline leg")
     return ap.parse_args()
@@ -74,9 +86,25 @@ def frame_yaw(global_frame: int) -> float:
     return -20.0 + 40.0 * ((global_frame % 8) / 7.0)  # 8 distinct cameras, yaw +-20 deg
 
 
-def config_dict(args, wl, extra=None):
-    c = {"workload": wl.name, "frames_per_rank_per_step": args.frames, "P": wl.n_avatar + wl.n_scene,
-         "image": f"{wl.width}x{wl.height}", "sh_degree": wl.sh_degree, "backward": wl.backward,
+def resolve_pattern(args, wl) -> str:
+    can_five = wl.backward and wl.n_avatar > 0 and wl.n_scene > 0 and wl.sh_degree == 0
+    if args.pattern == "five" and not can_five:
+        raise SystemExit(f"bench.py: workload {wl.name} cannot run the five-render pattern")
+    return "five" if (args.pattern == "five" or (args.pattern == "auto" and can_five)) else "single"
+
+
+def workload_label(wl, pattern) -> str:
+    if pattern == "five":
+        return (f"{wl.name} as ExAvatar trains it: five renders per frame (model.py:81-162: scene | human rand-bg | "
+                f"cat(scene.detach(),human) | human_refined | cat(scene.detach(),human_refined)), fwd+bwd each")
+    return wl.name
+
+
+def config_dict(args, wl, pattern, extra=None):
+    c = {"workload": workload_label(wl, pattern), "pattern": pattern, "frames_per_rank_per_step": args.frames,
+         "renders_per_frame": 5 if pattern == "five" else 1, "P": wl.n_avatar + wl.n_scene,
+         "P_scene": wl.n_scene, "P_human": wl.n_avatar, "image": f"{wl.width}x{wl.height}", "sh_degree": wl.sh_degree,
+         "backward": wl.backward,
          "parallelism": f"frames sharded over {args.gpus} rank(s), one gradient all-reduce per step" if args.gpus > 1
          else "single GPU", "l2": "256 MiB L2 flush before every timed step (outside the event pairs)"}
     if extra:
@@ -87,32 +115,51 @@ def config_dict(args, wl, extra=None):
 # ---------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the CPU oracle behind the reference-facing call
 # ---------------------------------------------------------------------------------------------------------------
-def cpu_frame_fn(wl_name, seed=0):
-    """Returns a closure running one frame (fwd [+bwd]) of the workload on the CPU oracle through GaussianRenderer."""
+def cpu_frame_fn(wl_name, pattern, seed=0):
+    """Returns (closure running one frame of the pattern on the CPU oracle through GaussianRenderer, threads used)."""
     from oracle import oracle as O
     from exavatar_release_b200.renderer import GaussianRenderer, render_settings
 
     wl = WORKLOADS[wl_name]
     O.set_num_threads(os.cpu_count() or 1)
-    assets = make_assets(wl_name, seed=seed)
-    gi = make_grad_image(wl_name, seed)
     renderer = GaussianRenderer(rasterizer_cls=O.OracleRasterizer, settings_cls=O.OracleSettings)
     bg = torch.ones(3)
-    use_sh = wl.sh_degree > 0
+    shape = (wl.height, wl.width)
 
-    def frame(i):
-        cam = look_at_cam_param(frame_yaw(i), (wl.height, wl.width))
-        leaves = {k: v.clone().requires_grad_(wl.backward) for k, v in assets.items()}
-        if use_sh:  # C3: colours from SH inside the rasteriser
-            st = render_settings((wl.height, wl.width), cam, bg, O.OracleSettings)._replace(sh_degree=wl.sh_degree)
-            m2 = torch.zeros(leaves["mean_3d"].shape[0], 3, requires_grad=wl.backward)
-            img = O.OracleRasterizer(st)(means3D=leaves["mean_3d"], means2D=m2, opacities=leaves["opacity"],
-                                         shs=leaves["shs"], scales=leaves["scale"], rotations=leaves["rotation"])[0]
-        else:
-            img = renderer(leaves, (wl.height, wl.width), cam, bg)["img"]
-        if wl.backward:
-            (img * gi).sum().backward()
-        return float(img.detach().sum())
+    if pattern == "five":
+        scene, human, refined = make_population_assets(wl_name, seed=seed)
+        gis = [make_grad_image(wl_name, 10 + j) for j in range(5)]
+        bg_r = torch.tensor(BG_RAND)
+
+        def frame(i):
+            cam = look_at_cam_param(frame_yaw(i), shape)
+            lv = {n: {k: v.clone().requires_grad_() for k, v in a.items()} for n, a in
+                  (("scene", scene), ("human", human), ("refined", refined))}
+            cat = lambda a, b: {k: torch.cat((a[k].detach(), b[k])) for k in a}  # model.py:117-125
+            imgs = [renderer(lv["scene"], shape, cam)["img"], renderer(lv["human"], shape, cam, bg_r)["img"],
+                    renderer(cat(lv["scene"], lv["human"]), shape, cam)["img"],
+                    renderer(lv["refined"], shape, cam, bg_r)["img"],
+                    renderer(cat(lv["scene"], lv["refined"]), shape, cam)["img"]]
+            sum((im * g).sum() for im, g in zip(imgs, gis)).backward()
+            return float(imgs[2].detach().sum())
+    else:
+        assets = make_assets(wl_name, seed=seed)
+        gi = make_grad_image(wl_name, seed)
+        use_sh = wl.sh_degree > 0
+
+        def frame(i):
+            cam = look_at_cam_param(frame_yaw(i), shape)
+            leaves = {k: v.clone().requires_grad_(wl.backward) for k, v in assets.items()}
+            if use_sh:  # C3: colours from SH inside the rasteriser
+                st = render_settings(shape, cam, bg, O.OracleSettings)._replace(sh_degree=wl.sh_degree)
+                m2 = torch.zeros(leaves["mean_3d"].shape[0], 3, requires_grad=wl.backward)
+                img = O.OracleRasterizer(st)(means3D=leaves["mean_3d"], means2D=m2, opacities=leaves["opacity"],
+                                             shs=leaves["shs"], scales=leaves["scale"], rotations=leaves["rotation"])[0]
+            else:
+                img = renderer(leaves, shape, cam, bg)["img"]
+            if wl.backward:
+                (img * gi).sum().backward()
+            return float(img.detach().sum())
 
     # "all the host threads it can use": OpenMP scaling of the oracle saturates (atomics in the backward), so pick the
     # fastest thread count among a few candidates instead of blindly using every core
@@ -134,21 +181,28 @@ def run_reference(args):
     if rank != 0:
         return 0
     wl = WORKLOADS[args.workload]
-    frame, threads = cpu_frame_fn(args.workload)
-    # bounded sample: one frame per step
-    for i in range(args.warmup):
+    pattern = resolve_pattern(args, wl)
+    frame, threads = cpu_frame_fn(args.workload, pattern)
+    # bounded sample: one training frame per step; the step count shrinks if a frame is slow so the arm ends in minutes
+    t0 = time.perf_counter()
+    frame(0)
+    one = time.perf_counter() - t0
+    warm = max(0, min(args.warmup, int(20.0 / max(one, 1e-3))))
+    steps = max(1, min(args.steps, int(120.0 / max(one, 1e-3))))
+    for i in range(warm):
         frame(i)
     t0 = time.perf_counter()
-    for i in range(args.steps):
+    for i in range(steps):
         frame(i)
     dt = time.perf_counter() - t0
-    fps = args.steps / dt
-    sample = f"1 frame of {wl.name} per step ({'fwd+bwd' if wl.backward else 'fwd'}), {args.steps} steps, {threads} threads"
-    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+    fps = steps / dt
+    what = "5 renders fwd+bwd" if pattern == "five" else ("fwd+bwd" if wl.backward else "fwd")
+    sample = f"1 frame of {wl.name} per step ({what}), {steps} timed steps, {threads} threads"
+    line = {"impl": "reference", "metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": warm, "ms_per_step": 1e3 * dt / steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": config_dict(args, wl, {"frames_per_rank_per_step": 1, "parallelism": f"{threads} host threads (OpenMP)",
-                                              "l2": "n/a (CPU)"}),
+            "config": config_dict(args, wl, pattern, {"frames_per_rank_per_step": 1,
+                                                      "parallelism": f"{threads} host threads (OpenMP)", "l2": "n/a (CPU)"}),
             "cpu_baseline": {"value": fps, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample},
             "e2e": {"value": fps, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
@@ -245,45 +299,475 @@ class ClockSampler:
 
 
 # ---------------------------------------------------------------------------------------------------------------
-# B200 arm
+# B200 arm: shared plumbing
 # ---------------------------------------------------------------------------------------------------------------
-def run_b200(args):
-    import torch.distributed as dist
-    from exavatar_release_b200 import _lib as L
+class Env:
+    """Process-wide state of the B200 arm: ranks, device, the loaded library, timing helpers."""
+
+    def __init__(self, args):
+        import torch.distributed as dist
+        from exavatar_release_b200 import _lib as L
+        self.dist = dist
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.local = int(os.environ.get("LOCAL_RANK", "0"))
+        if not torch.cuda.is_available():
+            raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
+        torch.cuda.set_device(self.local)
+        self.dev = torch.device("cuda", self.local)
+        if self.world > 1:
+            dist.init_process_group("nccl", device_id=self.dev)
+        self.lib = L.load()
+        self.flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=self.dev)
+        self.args = args
+
+    def barrier(self):
+        torch.cuda.synchronize(self.dev)
+        if self.world > 1:
+            self.dist.barrier()
+
+    def timed(self, fn, steps):
+        """K steps, each bracketed by CUDA events after an L2 flush; returns (ms summed, max over ranks; wall s; launches)."""
+        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
+        self.barrier()
+        l0 = self.lib.b2r_launch_count()
+        t0 = time.perf_counter()
+        for s in range(steps):
+            self.flush_buf.zero_()
+            ev[s][0].record()
+            fn()
+            ev[s][1].record()
+        self.barrier()
+        wall = time.perf_counter() - t0
+        ms = sum(a.elapsed_time(b) for a, b in ev)
+        t = torch.tensor([ms], device=self.dev, dtype=torch.float64)
+        if self.world > 1:
+            self.dist.all_reduce(t, op=self.dist.ReduceOp.MAX)
+        return float(t.item()), wall, self.lib.b2r_launch_count() - l0
+
+    def capture(self, body):
+        """Warm `body` on a side stream, then capture it into a CUDA graph; returns (graph, launches of this library)."""
+        side = torch.cuda.Stream(self.dev)
+        side.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(side):
+            body()
+        torch.cuda.current_stream(self.dev).wait_stream(side)
+        torch.cuda.synchronize(self.dev)
+        g = torch.cuda.CUDAGraph()
+        l0 = self.lib.b2r_launch_count()
+        with torch.cuda.graph(g):
+            body()
+        return g, self.lib.b2r_launch_count() - l0
+
+    def profile_read(self, reset=True):
+        ms_arr = (C.c_double * 9)()
+        cnt_arr = (C.c_uint64 * 9)()
+        self.lib.b2r_profile_read(ms_arr, cnt_arr, 1 if reset else 0)
+        return {self.lib.b2r_kernel_name(i).decode(): {"ms_avg": (ms_arr[i] / cnt_arr[i]) if cnt_arr[i] else 0.0,
+                                                       "launches": int(cnt_arr[i])} for i in range(9)}
+
+
+def peaks_and_traffic(workload_key, dom):
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(workload_key, {}).get(dom)
+    except Exception:
+        pass
+    return peaks, traffic
+
+
+def roofline_dict(per_kernel, algo, workload_key, extra):
+    dom = max(("composite_fwd", "composite_bwd"), key=lambda k: per_kernel[k]["ms_avg"] * (1 if per_kernel[k]["launches"] else 0))
+    peaks, traffic = peaks_and_traffic(workload_key, dom)
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    ms = per_kernel[dom]["ms_avg"]
+    ach = algo[dom] / (ms * 1e-3) / 1e9 if ms > 0 else 0.0
+    other = "composite_fwd" if dom == "composite_bwd" else "composite_bwd"
+    oms = per_kernel[other]["ms_avg"]
+    r = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
+         "frac": ach / peak if peak else None, "traffic": traffic,
+         "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
+         "algorithmic_bytes_per_launch": algo[dom], "kernel_ms_avg": ms,
+         "other_composite": {"kernel": other, "kernel_ms_avg": oms, "algorithmic_bytes_per_launch": algo[other],
+                             "frac": (algo[other] / (oms * 1e-3) / 1e9 / peak) if oms > 0 and peak else None},
+         "binding_bound": "instruction issue (ALU/SFU/shared memory), not HBM -- see DESIGN.md section 5",
+         "per_kernel_ms": {k: round(v["ms_avg"], 5) for k, v in per_kernel.items() if v["launches"]},
+         "per_kernel_launches": {k: v["launches"] for k, v in per_kernel.items() if v["launches"]}}
+    r.update(extra)
+    return r
+
+
+def consumed_units(stt):
+    """List entries staged per TILE by the composites, from the status block (units documented in b200raster.h)."""
+    return stt["consumed_fwd"] / stt.get("consumed_fwd_div", 4.0), stt["consumed_bwd"] / stt.get("consumed_bwd_div", 4.0)
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# pattern "five": ExAvatar's training frame
+# ---------------------------------------------------------------------------------------------------------------
+def make_five_engine(kind, Ps, Ph, W, H, caps, dev):
+    from exavatar_release_b200 import plan as PL
+    if kind == "merged" and hasattr(PL, "MergedFivePlan"):
+        return PL.MergedFivePlan(Ps, Ph, W, H, caps, dev), "merged"
+    return PL.FiveRenderPlan(Ps, Ph, W, H, caps, dev), "separate"
+
+
+def bench_five(env, args, wl, wl_key):
+    from exavatar_release_b200 import rasterizer as RZ
+    from exavatar_release_b200.renderer import GaussianRenderer, render_settings
+    from exavatar_release_b200.sharding import shard_frames
+    dev, lib, world, rank = env.dev, env.lib, env.world, env.rank
+    F, K, Wm = args.frames, args.steps, max(args.warmup, 3)
+    H, Wd = wl.height, wl.width
+    N = H * Wd
+    Ps, Ph = wl.n_scene, wl.n_avatar
+    bg_w = torch.ones(3, device=dev)
+    bg_r = torch.tensor(BG_RAND, device=dev)
+    scene_a, human_a, refined_a = make_population_assets(wl_key, seed=0, device=dev)
+
+    def cams_for(frames):
+        cs = [look_at_cam_param(frame_yaw(f), (H, Wd), device=dev) for f in frames]
+        return cs, [render_settings((H, Wd), c, bg_w) for c in cs], [render_settings((H, Wd), c, bg_r) for c in cs]
+
+    weak_frames = [rank * F + f for f in range(F)]
+    cams, st_w, st_r = cams_for(weak_frames)
+    g5 = [{r: make_grad_image(wl_key, seed=10 * f + j, device=dev) for j, r in enumerate(FIVE)} for f in range(8)]
+
+    # ---- capacities: one probing pass with generous room, then the real engine ----
+    probe, _ = make_five_engine(args.engine, Ps, Ph, Wd, H, None, dev)
+    probe.set_scene(scene_a)
+    need = {}
+    for f in range(len(cams)):
+        probe.frame(("probe", f), st_w[f], st_r[f], scene_a, human_a, refined_a, g5[f % 8], accumulate=False)
+        torch.cuda.synchronize(dev)
+        for k, v in probe.dups().items():
+            need[k] = max(need.get(k, 0), v)
+    del probe
+    torch.cuda.empty_cache()
+    caps = {k: int(v * 1.1) + 4096 for k, v in need.items()}
+    engine, engine_kind = make_five_engine(args.engine, Ps, Ph, Wd, H, caps, dev)
+
+    stats = {"grad_accum": torch.zeros(Ps, device=dev), "count": torch.zeros(Ps, device=dev),
+             "radius_max": torch.zeros(Ps, device=dev)}  # SceneGaussian.xyz_grad_accum / track_cnt / radius_max
+
+    def body_for(frame_ids, sts_w, sts_r, scale=None):
+        gimgs = g5 if scale is None else [{r: g * scale for r, g in gf.items()} for gf in g5]
+
+        def body():
+            engine.set_scene(scene_a)
+            for j, f in enumerate(frame_ids):
+                engine.frame(("f", f), sts_w[j], sts_r[j], scene_a, human_a, refined_a, gimgs[f % 8], accumulate=(j > 0),
+                             densify=stats)
+            engine.reduce()
+        return body
+
+    body = body_for(weak_frames, st_w, st_r)
+    graph, launches_per_step = (None, 0)
+    if not args.no_graph:
+        graph, launches_per_step = env.capture(body)
+
+    flat = engine.flat_bucket()  # ONE flat fp32 buffer: every per-Gaussian gradient of the three parameter sets
+
+    def collectives():
+        """one gradient all-reduce per step + the small densification-statistics reduction
+        (module.py:111-113,155-157: xyz_grad_accum sum, track_cnt sum, radius_max max)."""
+        env.dist.all_reduce(flat)
+        env.dist.all_reduce(stats["grad_accum"])
+        env.dist.all_reduce(stats["count"])
+        env.dist.all_reduce(stats["radius_max"], op=env.dist.ReduceOp.MAX)
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            body()
+        if world > 1:
+            collectives()
+
+    for _ in range(Wm):
+        step()
+    clocks = ClockSampler(env.local) if rank == 0 else None
+    ms_total, wall, launches_eager = env.timed(step, K)
+    if clocks is not None and len(clocks.samples) < 20:
+        t_end = time.perf_counter() + 0.5
+        while time.perf_counter() < t_end and len(clocks.samples) < 40:
+            step()
+            torch.cuda.synchronize(dev)
+        clocks.window = "timed region, then the same step replayed untimed until >= 20 NVML samples were taken"
+    clk = clocks.stop() if clocks else None
+    if engine.overflowed():
+        raise SystemExit("bench.py: duplicate capacity overflowed; results invalid")
+    launches = launches_eager if graph is None else K * launches_per_step
+    fps = world * F * K / (ms_total * 1e-3)
+
+    # ---- collective cost alone (N > 1): the same reductions, timed without the renders ----
+    coll = None
+    if world > 1:
+        for _ in range(3):
+            collectives()
+        ms_c, _, _ = env.timed(collectives, 10)
+        coll = {"ms_per_step": ms_c / 10, "bucket_bytes": int(flat.numel() * 4),
+                "what": "ncclAllReduce(sum) of the flat gradient bucket + 3 small densification-stat all-reduces (sum, sum, max)"}
+
+    # ---- per-kernel durations: the renders of one step, one at a time, in-library events ----
+    lib.b2r_profile_enable(1)
+    env.profile_read()
+    prof_steps = min(K, 3)
+    cons = []
+    for s in range(prof_steps):
+        env.flush_buf.zero_()
+        engine.set_scene(scene_a)
+        for j, f in enumerate(weak_frames):
+            engine.frame(("f", f), st_w[j], st_r[j], scene_a, human_a, refined_a, g5[f % 8], accumulate=(j > 0),
+                         densify=stats, serial=True)
+            if s == 0:
+                cons.append(engine.consumed())
+    per_kernel = env.profile_read()
+    lib.b2r_profile_enable(0)
+    tiles = ((Wd + 15) // 16) * ((H + 15) // 16)
+    # average over the composite launches of a frame (5 forward, 5 backward)
+    Cf = sum(sum(c["fwd"]) for c in cons) / sum(len(c["fwd"]) for c in cons)
+    Cb = sum(sum(c["bwd"]) for c in cons) / sum(len(c["bwd"]) for c in cons)
+    algo = {"composite_fwd": 44.0 * Cf + 24.0 * N + 8.0 * tiles, "composite_bwd": 84.0 * Cb + 20.0 * N}
+    frame_kernel_ms = sum(v["ms_avg"] * v["launches"] for v in per_kernel.values()) / (prof_steps * F)
+    roofline = roofline_dict(per_kernel, algo, wl_key + ("/five" if True else ""), {
+        "sum_kernel_ms_per_training_frame": frame_kernel_ms, "consumed_fwd_per_render": Cf, "consumed_bwd_per_render": Cb,
+        "dups_needed": need, "note": "per-launch averages over the composite launches of a training frame"})
+
+    # ---- strong scaling (configs[3] literally): global batch of 8 frames over the ranks ----
+    strong = None
+    if world > 1:
+        G = 8
+        mine = shard_frames(G, rank, world)
+        cs, sw, sr = cams_for(mine)
+        sbody = body_for(mine, sw, sr, scale=1.0 / G) if mine else (lambda: None)  # loss pre-divided (train.py:43)
+        sgraph = None
+        if mine and not args.no_graph:
+            sgraph, _ = env.capture(sbody)
+
+        def sstep():
+            if sgraph is not None:
+                sgraph.replay()
+            else:
+                sbody()
+            collectives()
+
+        for _ in range(3):
+            sstep()
+        ks = max(3, min(K, 20))
+        ms_s, _, _ = env.timed(sstep, ks)
+        strong = {"value": G * ks / (ms_s * 1e-3), "unit": UNIT, "global_batch": G, "frames_per_rank": len(mine),
+                  "ms_per_step": ms_s / ks, "steps": ks,
+                  "semantics": "rank r renders frames r::N of the 8-frame batch, dL/dimage pre-divided by 8 "
+                               "(loss.mean(), train.py:43); gradient bucket + densify statistics all-reduced"}
+
+    # ---- end to end through the public API with host buffers ----
+    e2e, e2e_eager = None, None
+    if not args.no_e2e:
+        e2e, e2e_eager = e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_a, max(caps.values()),
+                                  collectives if world > 1 else None)
+
+    extra = {"cuda_graph": graph is not None, "dup_capacity": caps, "engine": engine_kind,
+             "streams": engine.describe()}
+    return {"value": fps, "ms_per_step": ms_total / K, "clocks": clk, "launches": int(launches), "roofline": roofline,
+            "e2e": e2e, "e2e_eager": e2e_eager, "strong_scaling": strong, "collective": coll, "wall": wall, "config": extra,
+            "warmup": Wm}
+
+
+def e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_a, cap, collectives):
+    """ExAvatar's training frame through the PUBLIC API with pinned host buffers (see module docstring)."""
+    from exavatar_release_b200 import rasterizer as RZ
+    from exavatar_release_b200.renderer import GaussianRenderer
+    dev, world = env.dev, env.world
+    F, K = args.frames, args.steps
+    H, Wd = wl.height, wl.width
+    N = H * Wd
+    bg_w = torch.ones(3, device=dev)
+    bg_r = torch.tensor(BG_RAND, device=dev)
+    sets = {"scene": scene_a, "human": human_a, "refined": refined_a}
+    host = {n: {k: v.cpu().pin_memory() for k, v in a.items()} for n, a in sets.items()}
+    host_grads = {n: {k: torch.empty_like(v).pin_memory() for k, v in a.items()} for n, a in host.items()}
+    host_targets = [torch.rand(3, H, Wd).pin_memory() for _ in range(F)]
+    host_loss = torch.empty(F).pin_memory()
+    nbytes = lambda d: sum(v.numel() * 4 for a in d.values() for v in a.values())
+    h2d = nbytes(host) + F * 3 * N * 4
+    d2h = nbytes(host_grads) + F * 4
+    renderer = GaussianRenderer()
+    S = max(1, min(args.lanes, F))
+    cat = lambda a, b: {k: torch.cat((a[k].detach(), b[k])) for k in a}  # model.py:117-125
+
+    def frame_loss(lv, f, tgt, use_cached_settings):
+        kw_w = {"raster_settings": st_w[f]} if use_cached_settings else {}
+        kw_r = {"raster_settings": st_r[f]} if use_cached_settings else {}
+        shape = (H, Wd)
+        imgs = [renderer(lv["scene"], shape, cams[f], **kw_w)["img"],
+                renderer(lv["human"], shape, cams[f], bg_r, **kw_r)["img"],
+                renderer(cat(lv["scene"], lv["human"]), shape, cams[f], **kw_w)["img"],
+                renderer(lv["refined"], shape, cams[f], bg_r, **kw_r)["img"],
+                renderer(cat(lv["scene"], lv["refined"]), shape, cams[f], **kw_w)["img"]]
+        return sum(torch.nn.functional.l1_loss(im, tgt) for im in imgs), imgs
+
+    keep_alive = []
+    h2d_s, d2h_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    lane_s = [torch.cuda.Stream(dev) for _ in range(S)]
+
+    def body(use_cached_settings=True):
+        cur = torch.cuda.current_stream(dev)
+        for st_ in lane_s:
+            st_.wait_stream(cur)
+        d2h_s.wait_stream(cur)
+        h2d_s.wait_stream(cur)
+        with torch.cuda.stream(h2d_s):
+            params = {n: {k: v.to(dev, non_blocking=True) for k, v in a.items()} for n, a in host.items()}
+            ev_p = torch.cuda.Event()
+            ev_p.record(h2d_s)
+            tgts, ev_t = [], []
+            for f in range(F):
+                tgts.append(host_targets[f].to(dev, non_blocking=True))
+                e = torch.cuda.Event()
+                e.record(h2d_s)
+                ev_t.append(e)
+        keep_alive.append((params, tgts))
+        leaves = []
+        for st_ in lane_s:
+            st_.wait_event(ev_p)
+            with torch.cuda.stream(st_):
+                leaves.append({n: {k: v.detach().requires_grad_() for k, v in a.items()} for n, a in params.items()})
+        losses = []
+        for f in range(F):
+            fs, lv = lane_s[f % S], leaves[f % S]
+            with torch.cuda.stream(fs):
+                fs.wait_event(ev_t[f])
+                loss, imgs = frame_loss(lv, f, tgts[f], use_cached_settings)
+                loss.backward()
+                losses.append(loss.detach().reshape(1))
+                keep_alive.append((imgs, loss))
+        for st_ in lane_s:
+            cur.wait_stream(st_)
+        total = {n: {k: leaves[0][n][k].grad for k in host[n]} for n in host}
+        for lv in leaves[1:]:
+            if lv["scene"]["mean_3d"].grad is not None:
+                total = {n: {k: total[n][k] + lv[n][k].grad for k in host[n]} for n in host}
+        lvec = torch.cat(losses)
+        keep_alive.append((leaves, total, lvec))
+        done = torch.cuda.Event()
+        done.record(cur)
+        with torch.cuda.stream(d2h_s):
+            d2h_s.wait_event(done)
+            host_loss.copy_(lvec, non_blocking=True)
+            for n in host:
+                for k in host[n]:
+                    host_grads[n][k].copy_(total[n][k], non_blocking=True)
+        cur.wait_stream(d2h_s)
+        cur.wait_stream(h2d_s)
+
+    # ---- graph-captured step (fixed-capacity mode of the rasteriser: no polling) ----
+    RZ.set_fixed_capacity(cap)
+    side = torch.cuda.Stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        for _ in range(2):
+            body()
+            torch.cuda.synchronize(dev)
+            keep_alive.clear()
+    torch.cuda.current_stream(dev).wait_stream(side)
+    torch.cuda.synchronize(dev)
+    graph = None
+    if not args.no_graph:
+        try:
+            graph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(graph):
+                body()
+        except Exception as exc:
+            print(f"bench.py: e2e graph capture failed ({type(exc).__name__}: {exc}); timing the eager step", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize(dev)
+
+    def step():
+        if graph is not None:
+            graph.replay()
+        else:
+            body()
+            torch.cuda.synchronize(dev)
+            keep_alive.clear()
+        if collectives is not None:
+            collectives()
+
+    for _ in range(3):
+        step()
+    ke = max(3, min(K, 20))
+    ms_e, _, _ = env.timed(step, ke)
+    if args.trace_e2e and env.rank == 0:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            step()
+            torch.cuda.synchronize(dev)
+        prof.export_chrome_trace(args.trace_e2e)
+    if RZ.overflowed():
+        raise SystemExit("bench.py: e2e leg overflowed its fixed duplicate capacity; results invalid")
+    RZ.set_fixed_capacity(None)
+    e2e = {"value": world * F * ke / (ms_e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "upload": "per step: the three Gaussian parameter sets (scene, human, human_refined) + one target image per "
+                     "frame up; the summed gradients of the three sets + per-frame losses down",
+           "api": "5x GaussianRenderer.forward -> GaussianRasterizer (autograd) per frame, L1 loss on each image, one "
+                  "backward per frame, pinned host buffers; " + ("whole step captured in a CUDA graph, copies on forked streams"
+                                                                  if graph is not None else "eager, copies on side streams"),
+           "steps": ke, "lanes": S}
+
+    # ---- eager: the unmodified reference call shape, adaptive capacity, no graph ----
+    eager = None
+    if not args.no_eager:
+        del graph
+        keep_alive.clear()
+
+        def eager_step():
+            body(use_cached_settings=False)
+            torch.cuda.synchronize(dev)
+            keep_alive.clear()
+            if collectives is not None:
+                collectives()
+
+        for _ in range(2):
+            eager_step()
+        kk = max(2, min(K, 5))
+        t0 = time.perf_counter()
+        ms_g, _, _ = env.timed(eager_step, kk)
+        eager = {"value": world * F * kk / (ms_g * 1e-3), "unit": UNIT, "steps": kk,
+                 "host_ms_per_render": ms_g / (kk * F * 5),
+                 "api": "GaussianRenderer.forward(assets, img_shape, cam_param, bg) exactly as module.py:592 (camera matrices "
+                        "rebuilt per call, no cached settings), adaptive duplicate capacity, no CUDA graph"}
+    return e2e, eager
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# pattern "single": one render per frame (round-1 bench; C1 / C3 / C5 and the `single_render` key)
+# ---------------------------------------------------------------------------------------------------------------
+def bench_single(env, args, wl, wl_key, brief=False):
     from exavatar_release_b200 import rasterizer as RZ
     from exavatar_release_b200.plan import FrameLanes
     from exavatar_release_b200.renderer import GaussianRenderer, render_settings
-
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
-    if not torch.cuda.is_available():
-        raise SystemExit("bench.py: no CUDA device; the B200 arm has no CPU fallback (use --impl reference)")
-    torch.cuda.set_device(local)
-    dev = torch.device("cuda", local)
-    if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
-    lib = L.load()
-    wl = WORKLOADS[args.workload]
-    F, K, Wm = args.frames, args.steps, max(args.warmup, 3)
+    dev, lib, world, rank = env.dev, env.lib, env.world, env.rank
+    dist = env.dist
+    F, K, Wm = args.frames, (min(args.steps, 10) if brief else args.steps), max(args.warmup, 3)
     P, H, Wd = wl.n_avatar + wl.n_scene, wl.height, wl.width
     N = H * Wd
     use_sh = wl.sh_degree > 0
     M = (wl.sh_degree + 1) ** 2 if use_sh else 0
     bg = torch.ones(3, device=dev)
 
-    # one Gaussian set per rank (the replicated parameters), F cameras per step
-    assets = make_assets(args.workload, seed=0, device=dev)
-    gimgs = [make_grad_image(args.workload, seed=f, device=dev) for f in range(F)]
+    assets = make_assets(wl_key, seed=0, device=dev)
+    gimgs = [make_grad_image(wl_key, seed=f, device=dev) for f in range(F)]
     cams = [look_at_cam_param(frame_yaw(rank * F + f), (H, Wd), device=dev) for f in range(F)]
     settings = []
     for c in cams:
         st = render_settings((H, Wd), c, bg)
         settings.append(st._replace(sh_degree=wl.sh_degree) if use_sh else st)
 
-    flush_buf = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    # ---- capacity: learn the duplicate counts through the autograd front-end (exact mode) ----
     def public_frame(f, leaves=None, grad=True):
         lv = leaves or {k: v.detach().requires_grad_(wl.backward and grad) for k, v in assets.items()}
         m2 = torch.zeros(P, 3, device=dev, requires_grad=wl.backward and grad)
@@ -295,7 +779,7 @@ def run_b200(args):
     dups = []
     with torch.no_grad():
         for f in range(F):
-            img, _, _ = public_frame(f, grad=False)
+            public_frame(f, grad=False)
             dups.append(RZ._state(dev).predicted[(P, Wd, H)])
     cap = int(max(dups) * 1.1) + 4096
 
@@ -308,19 +792,9 @@ def run_b200(args):
     def step_body():
         lanes.step(scenes, gimgs, backward=wl.backward)
 
-    graph = None
+    graph, launches_per_step = (None, 0)
     if not args.no_graph:
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            step_body()  # warm caches / attribute calls before capture
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        graph = torch.cuda.CUDAGraph()
-        l0 = lib.b2r_launch_count()
-        with torch.cuda.graph(graph):
-            step_body()
-        launches_per_step = lib.b2r_launch_count() - l0  # kernels of this library recorded into the graph
+        graph, launches_per_step = env.capture(step_body)
 
     def step():
         if graph is not None:
@@ -330,37 +804,11 @@ def run_b200(args):
         if world > 1 and wl.backward:
             dist.all_reduce(bucket)
 
-    def barrier():
-        torch.cuda.synchronize(dev)
-        if world > 1:
-            dist.barrier()
-
-    def timed(fn, steps, count_launches=False):
-        ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(steps)]
-        barrier()
-        l0 = lib.b2r_launch_count()
-        t0 = time.perf_counter()
-        for s in range(steps):
-            flush_buf.zero_()
-            ev[s][0].record()
-            fn()
-            ev[s][1].record()
-        barrier()
-        wall = time.perf_counter() - t0
-        ms = sum(a.elapsed_time(b) for a, b in ev)
-        t = torch.tensor([ms], device=dev, dtype=torch.float64)
-        if world > 1:
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        return float(t.item()), wall, lib.b2r_launch_count() - l0
-
-    # ---- leg 1: device-resident value ----
     for _ in range(Wm):
         step()
-    clocks = ClockSampler(local) if rank == 0 else None
-    ms_total, wall, launches_eager = timed(step, K)
+    clocks = ClockSampler(env.local) if (rank == 0 and not brief) else None
+    ms_total, wall, launches_eager = env.timed(step, K)
     if clocks is not None and len(clocks.samples) < 20:
-        # The timed region lasts tens of milliseconds and one NVML query takes a few: keep the identical step running
-        # (untimed) until the sampler has seen enough of this load
         t_end = time.perf_counter() + 0.5
         while time.perf_counter() < t_end and len(clocks.samples) < 40:
             for _ in range(4):
@@ -368,68 +816,44 @@ def run_b200(args):
             torch.cuda.synchronize(dev)
         clocks.window = "timed region, then the same step replayed untimed until >= 20 NVML samples were taken"
     clk = clocks.stop() if clocks else None
-    st_last = lanes.status()
-    if st_last["overflow"]:
+    if lanes.status()["overflow"]:
         raise SystemExit("bench.py: duplicate capacity overflowed; results invalid")
     launches = launches_eager if graph is None else K * launches_per_step
     fps = world * F * K / (ms_total * 1e-3)
+    if brief:
+        return {"value": fps, "ms_per_step": ms_total / K, "workload": wl.name, "frames_per_rank_per_step": F, "lanes": S,
+                "steps": K, "unit": UNIT}
 
-    # ---- leg 2: per-kernel durations (same step, eager, in-library events) ----
+    # ---- per-kernel durations (same step, eager, in-library events) ----
     lib.b2r_profile_enable(1)
-    import ctypes as C
-    ms_arr = (C.c_double * 9)()
-    cnt_arr = (C.c_uint64 * 9)()
-    lib.b2r_profile_read(ms_arr, cnt_arr, 1)
+    env.profile_read()
     cons_f, cons_b, ndups = [], [], []
     prof_steps = min(K, 5)
     for s in range(prof_steps):
-        flush_buf.zero_()
+        env.flush_buf.zero_()
         for f in range(F):
             plan.forward(scenes[f])
             if wl.backward:
                 plan.backward(scenes[f], gimgs[f], views, accumulate=(f > 0))
             if s == 0:
                 stt = plan.status()
-                cons_f.append(stt["consumed_fwd"]); cons_b.append(stt["consumed_bwd"]); ndups.append(stt["num_dups"])
-    lib.b2r_profile_read(ms_arr, cnt_arr, 1)
+                cf, cb = consumed_units(stt)
+                cons_f.append(cf); cons_b.append(cb); ndups.append(stt["num_dups"])
+    per_kernel = env.profile_read()
     lib.b2r_profile_enable(0)
-    per_kernel = {lib.b2r_kernel_name(i).decode(): {"ms_avg": (ms_arr[i] / cnt_arr[i]) if cnt_arr[i] else 0.0,
-                                                    "launches": int(cnt_arr[i])} for i in range(9)}
     tiles = ((Wd + 15) // 16) * ((H + 15) // 16)
-    # the composites run four quarter-tile CTAs per tile, each counting what it staged: /4 = per-tile list entries
-    Cf = sum(cons_f) / len(cons_f) / 4.0
-    Cb = sum(cons_b) / len(cons_b) / 4.0 if wl.backward else 0.0
-    # algorithmic bytes per launch (SURVEY section 8d / BASELINE.md section 4)
+    Cf = sum(cons_f) / len(cons_f)
+    Cb = sum(cons_b) / len(cons_b) if wl.backward else 0.0
     algo = {"composite_fwd": 44.0 * Cf + 24.0 * N + 8.0 * tiles, "composite_bwd": 84.0 * Cb + 20.0 * N}
-    dom = max(("composite_fwd", "composite_bwd"), key=lambda k: per_kernel[k]["ms_avg"])
-    peaks = {}
-    try:
-        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
-    except Exception:
-        pass
-    peak = float(peaks.get("hbm_gbs", 6650.0))
-    ach = algo[dom] / (per_kernel[dom]["ms_avg"] * 1e-3) / 1e9 if per_kernel[dom]["ms_avg"] > 0 else 0.0
-    traffic = None
-    try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get(args.workload, {}).get(dom)
-    except Exception:
-        pass
     frame_kernel_ms = sum(v["ms_avg"] * v["launches"] for v in per_kernel.values()) / (prof_steps * F)
-    roofline = {"bound": "hbm", "kernel": dom, "achieved": ach, "peak": peak, "unit": "GB/s",
-                "frac": ach / peak if peak else None, "traffic": traffic,
-                "peak_source": "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s",
-                "algorithmic_bytes_per_launch": algo[dom], "kernel_ms_avg": per_kernel[dom]["ms_avg"],
-                "binding_bound": "instruction issue (ALU/SFU/shared memory), not HBM -- see DESIGN.md section 5",
-                "per_kernel_ms": {k: round(v["ms_avg"], 5) for k, v in per_kernel.items() if v["launches"]},
-                "sum_kernel_ms_per_frame": frame_kernel_ms,
-                "consumed_fwd_per_frame": Cf, "consumed_bwd_per_frame": Cb, "dups_per_frame": sum(ndups) / len(ndups)}
+    roofline = roofline_dict(per_kernel, algo, wl_key, {
+        "sum_kernel_ms_per_frame": frame_kernel_ms, "consumed_fwd_per_frame": Cf, "consumed_bwd_per_frame": Cb,
+        "dups_per_frame": sum(ndups) / len(ndups)})
 
-    # ---- leg 3: end to end through the public API with host buffers ----
+    # ---- end to end through the public API with host buffers ----
     e2e = None
     if not args.no_e2e:
         host_assets = {k: v.cpu().pin_memory() for k, v in assets.items() if (k != "rgb" or not use_sh)}
-        if use_sh:
-            host_assets.pop("rgb", None)
         host_targets = [torch.rand(3, H, Wd).pin_memory() for _ in range(F)]
         host_grads = {k: torch.empty_like(v).pin_memory() for k, v in host_assets.items()}
         host_m2 = torch.empty(P, 3).pin_memory()
@@ -438,11 +862,6 @@ def run_b200(args):
         h2d = F * (sum(v.numel() * 4 for v in host_assets.values()) + 3 * N * 4)
         d2h = F * ((sum(v.numel() * 4 for v in host_grads.values()) + P * 12 + 4) if wl.backward else 3 * N * 4)
         host_img = torch.empty(3, H, Wd).pin_memory()
-
-        # The user's whole step -- pinned H2D of every frame's inputs, GaussianRenderer forward, loss, autograd backward,
-        # D2H of loss + gradients -- is captured once in a CUDA graph through the PUBLIC API (fixed-capacity mode of the
-        # rasteriser: no polling, see rasterizer.set_fixed_capacity) and replayed per step; inside the graph the
-        # copies of frame f+1 / f-1 run on forked streams beside frame f's kernels.  Host cost per step: one launch.
         RZ.set_fixed_capacity(cap)
         h2d_s, d2h_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
         lane_s = [torch.cuda.Stream(dev) for _ in range(S)] if S > 1 else None
@@ -610,7 +1029,7 @@ def run_b200(args):
         for _ in range(3):
             e2e_step()
         ke = max(3, min(K, 20))
-        ms_e, _, _ = timed(e2e_step, ke)
+        ms_e, _, _ = env.timed(e2e_step, ke)
         if args.trace_e2e and rank == 0:  # after the timed region: one more step under the profiler
             from torch.profiler import ProfilerActivity, profile
             with profile(activities=[ProfilerActivity.CUDA]) as prof:
@@ -629,60 +1048,24 @@ def run_b200(args):
                          else "eager, copies on side streams"),
                "steps": ke}
 
-    # ---- optional leg: the five-render training frame of avatar/main/model.py:81-162 ----
-    five = None
-    if args.five_render and wl.backward and wl.n_avatar and wl.n_scene and not use_sh:
-        from exavatar_release_b200.plan import RENDERS, FiveRenderPlan
-        from exavatar_release_b200.synthetic import make_population_assets
-        scene_a, human_a, refined_a = make_population_assets(args.workload, seed=0, device=dev)
-        bg_rand = torch.tensor([0.3, 0.7, 0.2], device=dev)
-        st_w = [render_settings((H, Wd), c, bg) for c in cams]
-        st_r = [render_settings((H, Wd), c, bg_rand) for c in cams]
-        g5 = [{r: make_grad_image(args.workload, seed=10 * f + j, device=dev) for j, r in enumerate(RENDERS)} for f in range(F)]
-        probe = FiveRenderPlan(wl.n_scene, wl.n_avatar, Wd, H, {r: 8_000_000 for r in RENDERS}, dev)
-        probe.set_scene(scene_a)
-        need = {r: 0 for r in RENDERS}
-        for f in range(F):
-            probe.frame(f, st_w[f], st_r[f], scene_a, human_a, refined_a, g5[f], accumulate=False)
-            torch.cuda.synchronize(dev)
-            for r in RENDERS:
-                need[r] = max(need[r], probe.plans[r].status()["num_dups"])
-        del probe
-        fplan = FiveRenderPlan(wl.n_scene, wl.n_avatar, Wd, H, {r: int(need[r] * 1.1) + 4096 for r in RENDERS}, dev)
+    return {"value": fps, "ms_per_step": ms_total / K, "clocks": clk, "launches": int(launches), "roofline": roofline,
+            "e2e": e2e, "e2e_eager": None, "strong_scaling": None, "collective": None, "wall": wall,
+            "config": {"cuda_graph": graph is not None, "dup_capacity": cap, "lanes": S}, "warmup": Wm}
 
-        def five_body():
-            fplan.set_scene(scene_a)
-            for f in range(F):
-                fplan.frame(f, st_w[f], st_r[f], scene_a, human_a, refined_a, g5[f], accumulate=(f > 0))
-            return fplan.reduce()
 
-        side = torch.cuda.Stream(dev)
-        side.wait_stream(torch.cuda.current_stream(dev))
-        with torch.cuda.stream(side):
-            five_body()
-        torch.cuda.current_stream(dev).wait_stream(side)
-        torch.cuda.synchronize(dev)
-        g5graph = torch.cuda.CUDAGraph()
-        l0 = lib.b2r_launch_count()
-        with torch.cuda.graph(g5graph):
-            five_out = five_body()
-        five_launches = lib.b2r_launch_count() - l0
-        for _ in range(3):
-            g5graph.replay()
-        k5 = max(3, min(K, 10))
-        ms5, _, _ = timed(g5graph.replay, k5)
-        if fplan.overflowed():
-            raise SystemExit("bench.py: five-render leg overflowed its duplicate capacity")
-        five = {"value": world * F * k5 / (ms5 * 1e-3), "unit": "frames/s (5 renders, fwd+bwd, per frame)",
-                "renders_per_s": 5 * world * F * k5 / (ms5 * 1e-3), "launches_per_step": int(five_launches),
-                "P_scene": wl.n_scene, "P_human": wl.n_avatar, "dups_per_render": need,
-                "pattern": "scene | human (random bg) | cat(scene.detach(), human) | human_refined | "
-                           "cat(scene.detach(), human_refined); five streams per frame, one CUDA graph per step"}
+def run_b200(args):
+    env = Env(args)
+    wl = WORKLOADS[args.workload]
+    pattern = resolve_pattern(args, wl)
+    res = bench_five(env, args, wl, args.workload) if pattern == "five" else bench_single(env, args, wl, args.workload)
 
-    # ---- leg 4: CPU baseline on the host cores (rank 0) ----
+    single = None
+    if pattern == "five" and not args.no_single:  # continuity with round 1: BASELINE configs[1], one render per frame
+        single = bench_single(env, args, WORKLOADS["C2"], "C2", brief=True)
+
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only (the other ranks would idle)
-        frame, threads = cpu_frame_fn(args.workload)
+    if env.rank == 0 and env.world == 1 and not args.no_cpu_baseline:  # reported at N = 1 only
+        frame, threads = cpu_frame_fn(args.workload, pattern)
         frame(0)
         n, t0 = 0, time.perf_counter()
         while True:
@@ -690,20 +1073,21 @@ def run_b200(args):
             if time.perf_counter() - t0 > args.cpu_seconds or n >= 64:
                 break
         dt = time.perf_counter() - t0
+        what = "training frame(s) (5 renders fwd+bwd each)" if pattern == "five" else "frame(s)"
         cpu = {"value": n / dt, "unit": UNIT, "cores": threads, "kind": "port",
-               "sample": f"{n} frame(s) of {wl.name} on the CPU oracle (OpenMP, {threads} threads), {dt:.1f} s"}
+               "sample": f"{n} {what} of {wl.name} on the CPU oracle (OpenMP, {threads} threads), {dt:.1f} s"}
 
-    if rank == 0:
-        line = {"metric": METRIC, "value": fps, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": Wm,
-                "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-                "dtype": "f32", "data": "synthetic",
-                "config": config_dict(args, wl, {"cuda_graph": graph is not None, "dup_capacity": cap, "lanes": S,
-                                                 "frames_per_rank_per_step": F}),
-                "clocks": clk, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu, "five_render": five,
-                "wall_s_timed_region": wall}
+    if env.rank == 0:
+        cfg = config_dict(args, wl, pattern, res["config"])
+        line = {"metric": METRIC, "value": res["value"], "unit": UNIT, "n_gpus": env.world, "steps": args.steps,
+                "warmup": res["warmup"], "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": res["clocks"],
+                "e2e": res["e2e"], "gpu_launches": res["launches"], "roofline": res["roofline"], "cpu_baseline": cpu,
+                "e2e_eager": res["e2e_eager"], "strong_scaling": res["strong_scaling"], "collective": res["collective"],
+                "single_render": single, "wall_s_timed_region": res["wall"]}
         print(json.dumps(line), flush=True)
-    if world > 1:
-        dist.destroy_process_group()
+    if env.world > 1:
+        env.dist.destroy_process_group()
     return 0
 
 

@@ -63,6 +63,10 @@ class B2RBackwardArgs(C.Structure):
     ]
 
 
+# B2RStatus.consumed_fwd / consumed_bwd are sums over composite CTAs; four quarter-tile CTAs walk each tile's list
+CONSUMED_FWD_DIV = 4
+CONSUMED_BWD_DIV = 4
+
 B2R_BWD_ACCUMULATE = 1
 B2R_BWD_SCRATCH_ZEROED = 2
 

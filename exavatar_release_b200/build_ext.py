@@ -38,7 +38,28 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     extra = os.environ.get("B2R_NVCC_EXTRA", "").split()  # e.g. -DB2_DRAIN_UNROLL=8 for tuning experiments
-    cmd = [nvcc, *NVCC_FLAGS, *extra, *(["-Xptxas", "-v"] if ptxas_info else []), "-o", LIB, *sources()]
+    # one object per translation unit, compiled in parallel (no relocatable device code: kernels never call across
+    # files), then one link -- a full rebuild takes as long as the slowest file instead of the sum
+    from concurrent.futures import ThreadPoolExecutor
+    objdir = os.path.join(PKG, "build")
+    os.makedirs(objdir, exist_ok=True)
+    flags = [f for f in NVCC_FLAGS if f != "--shared"]
+    srcs = sources()
+    objs = [os.path.join(objdir, os.path.basename(s)[:-3] + ".o") for s in srcs]
+    hdr_t = max(os.path.getmtime(d) for d in glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(PKG, "..", "include", "b200raster.h")])
+
+    def compile_one(pair):
+        src, obj = pair
+        if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t) and not extra:
+            return
+        cmd = [nvcc, *flags, *extra, *(["-Xptxas", "-v"] if ptxas_info else []), "-c", "-o", obj, src]
+        if verbose:
+            print(" ".join(cmd), flush=True)
+        subprocess.check_call(cmd)
+
+    with ThreadPoolExecutor(max_workers=min(8, len(srcs))) as ex:
+        list(ex.map(compile_one, zip(srcs, objs)))
+    cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "--shared", "-o", LIB, *objs]
     if verbose:
         print(" ".join(cmd), flush=True)
     subprocess.check_call(cmd)

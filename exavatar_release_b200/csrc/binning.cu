@@ -522,7 +522,13 @@ constexpr int SORT_SMALL = SORT_CHUNK;  // capacity of the CTA-wide sort = chunk
 
 int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t st) {
   // the two-phase entry re-derives ranges and cursors for the capacity the caller finally chose
-  if (rescan) launch_tile_scan(cx, st);
+  // (never re-published to the host mirror: the count there belongs to the project phase that produced it, and another
+  // stream's render may be waiting on its own token in the same mirror)
+  if (rescan) {
+    Ctx quiet = cx;
+    quiet.status_mirror = nullptr;
+    launch_tile_scan(quiet, st);
+  }
   if (sc.P > 0) {
     ProfScope p(K_SCATTER, st);
     const size_t smem = (size_t)cx.tiles * 8;
@@ -535,21 +541,12 @@ int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t 
       launch_k(scatter_kernel, (sc.P + 255) / 256, 256, 0, st, true, sc, cx);
     }
   }
-  static int sms = 0;
-  if (sms == 0) {
-    int dev = 0;
-    cudaGetDevice(&dev);
-    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (sms <= 0) sms = 148;
-  }
+  const int sms = device_sm_count();
   constexpr int ST = 256;
   constexpr size_t cta_bytes = RadixSmem<SORT_SMALL, ST>::bytes, warp_bytes = (ST / 32) * WSORT_BYTES;
   constexpr size_t small_bytes = cta_bytes > warp_bytes ? cta_bytes : warp_bytes;
-  static bool attr_set = false;
-  if (!attr_set) {
-    cudaFuncSetAttribute(sort_mixed_kernel<SORT_SMALL, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes);
-    attr_set = true;
-  }
+  // function attributes are per device: set on every launch (cheap), so a process that drives several GPUs works
+  cudaFuncSetAttribute(sort_mixed_kernel<SORT_SMALL, ST>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)small_bytes);
   {
     ProfScope p(K_SORT_SMALL, st);
     launch_k(sort_mixed_kernel<SORT_SMALL, ST>, cx.tiles, ST, small_bytes, st, true, cx);

@@ -229,7 +229,9 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ wstage, float* __
 #pragma unroll
       for (int u = 0; u < 12; u++) {
         const int j = lane + 32 * u;
-        v[u] = j < n4 ? (MODE == 0 ? __ldg(g4 + j) : g4[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
+        // masked rows are never touched, not even read: with a detached prefix they lie before the output buffer
+        const bool rd = j < n4 && (MODE == 0 || ((row_mask >> (j / 12)) & 1u));
+        v[u] = rd ? (MODE == 0 ? __ldg(g4 + j) : g4[j]) : make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
 #pragma unroll
@@ -255,7 +257,7 @@ __device__ __forceinline__ void stage_rows(float* __restrict__ wstage, float* __
 #pragma unroll
       for (int u = 0; u < 8; u++) {
         const int e = e0 + 32 * u;
-        v[u] = e < total ? gptr[e] : 0.f;
+        v[u] = (e < total && (MODE == 0 || ((row_mask >> (e / L)) & 1u))) ? gptr[e] : 0.f;
       }
     }
 #pragma unroll
@@ -322,6 +324,7 @@ __device__ __forceinline__ void trace_end(unsigned long long t0, int n) {
 // behind the thousands of composite CTAs frame A still had queued (tools/lanes_timeline.py: 50-120 us gaps).  The
 // short, latency-bound kernels of the chain therefore run at high priority and the two composites at the default.
 int launch_priority(bool high);
+int device_sm_count();
 template <typename... KArgs, typename... Args>
 inline void launch_k(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool high,
                      Args... args) {

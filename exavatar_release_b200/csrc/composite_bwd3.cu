@@ -289,12 +289,7 @@ __global__ void __launch_bounds__(B3_THREADS, B3_MIN_BLOCKS) composite_bwd3_kern
   B2R_TRACE_END(nmax);
 }
 
-int launch_composite_bwd2(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, float* gacc, cudaStream_t st);
-
 int launch_composite_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, float* gacc, cudaStream_t st) {
-  // B2R_BWD_V2=1 selects the previous variant (composite_bwd2.cu) for A/B measurements
-  static const bool use_v2 = getenv("B2R_BWD_V2") != nullptr;
-  if (use_v2) return launch_composite_bwd2(sc, cx, a, gacc, st);
   if (!(a.flags & B2R_BWD_SCRATCH_ZEROED)) cudaMemsetAsync(gacc, 0, (size_t)(sc.P > 0 ? sc.P : 1) * 12 * sizeof(float), st);
   ProfScope p(K_COMPOSITE_BWD, st);
   if (a.dL_ddepth || a.dL_dalpha)

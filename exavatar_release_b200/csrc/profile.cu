@@ -23,6 +23,20 @@ int launch_priority(bool high) {
   return high ? r.greatest : r.least;
 }
 
+// SM count of the CURRENT device (cached per device ordinal: one process may drive several GPUs)
+int device_sm_count() {
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev < 0 || dev >= 64) dev = 0;
+  int v = cache[dev].load(std::memory_order_relaxed);
+  if (v == 0) {
+    if (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || v <= 0) v = 148;
+    cache[dev].store(v, std::memory_order_relaxed);
+  }
+  return v;
+}
+
 static std::atomic<int> g_prof_on{0};
 static std::atomic<unsigned long long> g_launches{0};
 static std::mutex g_mu;

@@ -326,11 +326,7 @@ int launch_project_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs&
     const bool use_sh = sc.shs != nullptr && a.dL_dshs != nullptr;
     const size_t smem = (use_sh ? (size_t)8 * 32 * ((sc.sh_coeffs * 3) | 1) * sizeof(float) : 0) +
                         (sc.skin_xyz ? (size_t)8 * 32 * (sc.skin_J | 1) * sizeof(float) : 0);
-    static bool attr_set = false;
-    if (!attr_set) {
-      cudaFuncSetAttribute(project_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);
-      attr_set = true;
-    }
+    cudaFuncSetAttribute(project_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 128 * 1024);  // per device
     launch_k(project_bwd_kernel, (sc.P + 255) / 256, 256, smem, st, true, sc, cx, a, gacc);
   }
   return check_launch();

@@ -85,7 +85,9 @@ class FramePlan:
         s = L.B2RStatus.from_buffer_copy(raw)
         return {"num_dups": int(s.num_dups), "dup_capacity": int(s.dup_capacity), "overflow": int(s.overflow),
                 "num_visible": int(s.num_visible), "consumed_fwd": int(s.consumed_fwd),
-                "consumed_bwd": int(s.consumed_bwd)}
+                "consumed_bwd": int(s.consumed_bwd),
+                # the composites count staged list entries per CTA; these divisors turn the sums into entries per TILE
+                "consumed_fwd_div": float(L.CONSUMED_FWD_DIV), "consumed_bwd_div": float(L.CONSUMED_BWD_DIV)}
 
 
 def grad_bucket(P: int, device, sh_coeffs: int = 0):
@@ -176,11 +178,17 @@ class FiveRenderPlan:
     field of the backward call (`first_row`), so the human part of their gradient is written straight into a
     human-sized bucket and nothing is computed-then-discarded on the host side.  Frames of a step accumulate into the
     same five buckets; `reduce()` folds them into the three parameter sets (scene, human, human_refined).
-    """
 
-    def __init__(self, P_scene: int, P_human: int, width: int, height: int, caps: Dict[str, int], device):
+    All gradients live in ONE flat fp32 buffer (`flat_bucket()`: scene | human | human_refined after `reduce()`), the
+    tensor a multi-GPU step all-reduces once.  `MergedFivePlan` below produces the same results
+    from two projection / binning passes instead of five.
+    """
+    PER = 3 + 3 + 1 + 3 + 4 + 3  # floats per Gaussian in a bucket
+
+    def __init__(self, P_scene: int, P_human: int, width: int, height: int, caps: Optional[Dict[str, int]], device):
         self.Ps, self.Ph = int(P_scene), int(P_human)
         self.device = torch.device(device)
+        caps = caps or {r: 8_000_000 for r in RENDERS}
         sizes = {"scene": self.Ps, "human": self.Ph, "scene_human": self.Ps + self.Ph, "human_refined": self.Ph,
                  "scene_human_refined": self.Ps + self.Ph}
         self.plans = {r: FramePlan(sizes[r], width, height, caps[r], device) for r in RENDERS}
@@ -188,12 +196,22 @@ class FiveRenderPlan:
         self.first_row = {"scene": 0, "human": 0, "scene_human": self.Ps, "human_refined": 0, "scene_human_refined": self.Ps}
         out_rows = {"scene": self.Ps, "human": self.Ph, "scene_human": self.Ph, "human_refined": self.Ph,
                     "scene_human_refined": self.Ph}
-        self.flat, self.views = {}, {}
-        for r in RENDERS:
-            self.flat[r], self.views[r] = grad_bucket(out_rows[r], device)
+        # one allocation: [scene | human | human_refined | scene_human | scene_human_refined]; the first three segments
+        # are what reduce() leaves the step's gradients in
+        order = ("scene", "human", "human_refined", "scene_human", "scene_human_refined")
+        self.all_flat = torch.zeros(self.PER * sum(out_rows[r] for r in order), dtype=torch.float32, device=device)
+        self.flat, self.views, o = {}, {}, 0
+        for r in order:
+            n = self.PER * out_rows[r]
+            self.flat[r], self.views[r] = _views_of(self.all_flat[o:o + n], out_rows[r])
+            o += n
+        self._reduced = self.PER * (self.Ps + 2 * self.Ph)
         f = lambda w: torch.empty(self.Ps + self.Ph, w, dtype=torch.float32, device=device)
         widths = {"mean_3d": 3, "opacity": 1, "scale": 3, "rotation": 4, "rgb": 3}
         self.cat = {r: {k: f(w) for k, w in widths.items()} for r in ("scene_human", "scene_human_refined")}
+
+    def describe(self) -> str:
+        return "five independent renders (project+bin+sort+composite each) on five CUDA streams per frame"
 
     def set_scene(self, scene_assets: Dict[str, torch.Tensor]) -> None:
         """Copies the (detached) scene Gaussians into the prefix of the two combined asset sets; once per step."""
@@ -212,26 +230,49 @@ class FiveRenderPlan:
         return self.cat[render]
 
     def frame(self, key, settings, settings_human_bg, scene, human, refined, g_colors: Dict[str, torch.Tensor],
-              accumulate: bool) -> None:
+              accumulate: bool, densify: Optional[Dict[str, torch.Tensor]] = None, serial: bool = False) -> None:
         """Forward + backward of the five renders of one frame.  `settings_human_bg` carries the random background of
-        the human-only renders (model.py:72).  `key` caches the per-(frame, render) scene descriptors."""
+        the human-only renders (model.py:72).  `key` caches the per-(frame, render) scene descriptors.  `densify`:
+        ExAvatar's densification statistics of the SCENE Gaussians, fed by the scene render (model.py:193, 279-285).
+        `serial`: all five on the caller's stream, one after the other (per-kernel profiling)."""
         cur = torch.cuda.current_stream(self.device)
         for r in RENDERS:
-            st = self.streams[r]
-            st.wait_stream(cur)
+            st = cur if serial else self.streams[r]
+            if not serial:
+                st.wait_stream(cur)
             with torch.cuda.stream(st):
                 plan = self.plans[r]
                 assets = self.assets_of(r, scene, human, refined)
                 sc = plan.scene((key, r), settings_human_bg if r in ("human", "human_refined") else settings, assets)
                 plan.forward(sc)
-                plan.backward(sc, g_colors[r], self.views[r], accumulate=accumulate, first_row=self.first_row[r])
-        for r in RENDERS:
-            cur.wait_stream(self.streams[r])
+                plan.backward(sc, g_colors[r], self.views[r], accumulate=accumulate, first_row=self.first_row[r],
+                              densify=densify if r == "scene" else None)
+        if not serial:
+            for r in RENDERS:
+                cur.wait_stream(self.streams[r])
+
+    def render_outputs(self, render: str):
+        """(color (3,H,W), alpha (1,H,W), radii) of one of the five renders of the last frame (valid until the next)."""
+        p = self.plans[render]
+        return p.color, p.alpha, p.radii
 
     def reduce(self):
-        """(scene, human, human_refined) flat gradient buckets of the step."""
-        return (self.flat["scene"], self.flat["human"] + self.flat["scene_human"],
-                self.flat["human_refined"] + self.flat["scene_human_refined"])
+        """(scene, human, human_refined) flat gradient buckets of the step (the first three segments of the flat bucket;
+        the combined renders' human rows are folded in, in a fixed order)."""
+        self.flat["human"].add_(self.flat["scene_human"])
+        self.flat["human_refined"].add_(self.flat["scene_human_refined"])
+        return self.flat["scene"], self.flat["human"], self.flat["human_refined"]
+
+    def flat_bucket(self) -> torch.Tensor:
+        return self.all_flat[: self._reduced]
+
+    def dups(self) -> Dict[str, int]:
+        return {r: p.status()["num_dups"] for r, p in self.plans.items()}
+
+    def consumed(self) -> Dict[str, list]:
+        st = [self.plans[r].status() for r in RENDERS]
+        return {"fwd": [s["consumed_fwd"] / s["consumed_fwd_div"] for s in st],
+                "bwd": [s["consumed_bwd"] / s["consumed_bwd_div"] for s in st]}
 
     def overflowed(self) -> bool:
         return any(p.status()["overflow"] for p in self.plans.values())
