@@ -66,7 +66,8 @@ def parse():
     ap.add_argument("--pattern", default="auto", choices=["auto", "five", "single"],
                     help="five: ExAvatar's five renders per training frame (needs both populations); single: one render")
     ap.add_argument("--frames", type=int, default=8, help="frames per rank per step")
-    ap.add_argument("--lanes", type=int, default=4, help="single pattern: frames in flight per rank (CUDA streams)")
+    ap.add_argument("--lanes", type=int, default=None,
+                    help="frames in flight per rank (CUDA streams): default 4 (single pattern), 3 (five pattern)")
     ap.add_argument("--engine", default=os.environ.get("B2R_FIVE_ENGINE", "merged"), choices=["merged", "separate"],
                     help="five pattern: merged = two projection/binning passes shared by the five renders (SURVEY 8f-3); "
                          "separate = five independent renders on five streams (round-1 FiveRenderPlan)")
@@ -87,10 +88,14 @@ def frame_yaw(global_frame: int) -> float:
 
 
 def resolve_pattern(args, wl) -> str:
+    if getattr(args, "_lanes_user", None) is None:
+        args._lanes_user = args.lanes
     can_five = wl.backward and wl.n_avatar > 0 and wl.n_scene > 0 and wl.sh_degree == 0
     if args.pattern == "five" and not can_five:
         raise SystemExit(f"bench.py: workload {wl.name} cannot run the five-render pattern")
-    return "five" if (args.pattern == "five" or (args.pattern == "auto" and can_five)) else "single"
+    pattern = "five" if (args.pattern == "five" or (args.pattern == "auto" and can_five)) else "single"
+    args.lanes = args._lanes_user if args._lanes_user is not None else (3 if pattern == "five" else 4)
+    return pattern
 
 
 def workload_label(wl, pattern) -> str:
@@ -438,7 +443,7 @@ def bench_five(env, args, wl, wl_key):
     cams, st_w, st_r = cams_for(weak_frames)
     g5 = [{r: make_grad_image(wl_key, seed=10 * f + j, device=dev) for j, r in enumerate(FIVE)} for f in range(8)]
 
-    # ---- capacities: one probing pass with generous room, then the real engine ----
+    # ---- capacities: one probing pass with generous room, then the real engines ----
     probe, _ = make_five_engine(args.engine, Ps, Ph, Wd, H, None, dev)
     probe.set_scene(scene_a)
     need = {}
@@ -450,28 +455,52 @@ def bench_five(env, args, wl, wl_key):
     del probe
     torch.cuda.empty_cache()
     caps = {k: int(v * 1.1) + 4096 for k, v in need.items()}
-    engine, engine_kind = make_five_engine(args.engine, Ps, Ph, Wd, H, caps, dev)
-
-    stats = {"grad_accum": torch.zeros(Ps, device=dev), "count": torch.zeros(Ps, device=dev),
-             "radius_max": torch.zeros(Ps, device=dev)}  # SceneGaussian.xyz_grad_accum / track_cnt / radius_max
+    # S training frames in flight ("lanes"): frame f runs on engine f mod S, each engine on its own stream with its own
+    # workspace, gradient bucket and densification statistics; the latency-bound head of one frame (project / scan /
+    # scatter / sort) then overlaps the composites of another.  Buckets are summed in a fixed order: deterministic.
+    S = max(1, min(args.lanes, F))
+    engines, engine_kind = [], None
+    for _ in range(S):
+        e, engine_kind = make_five_engine(args.engine, Ps, Ph, Wd, H, caps, dev)
+        engines.append(e)
+    engine = engines[0]
+    lane_streams = [torch.cuda.Stream(dev) for _ in range(S)]
+    mk_stats = lambda: {"grad_accum": torch.zeros(Ps, device=dev), "count": torch.zeros(Ps, device=dev),
+                        "radius_max": torch.zeros(Ps, device=dev)}
+    lane_stats = [mk_stats() for _ in range(S)]
+    stats = lane_stats[0]  # SceneGaussian.xyz_grad_accum / track_cnt / radius_max of the step (after the lane fold)
+    flat = engine.flat_bucket()  # ONE flat fp32 buffer: every per-Gaussian gradient of the three parameter sets
 
     def body_for(frame_ids, sts_w, sts_r, scale=None):
         gimgs = g5 if scale is None else [{r: g * scale for r, g in gf.items()} for gf in g5]
 
         def body():
-            engine.set_scene(scene_a)
-            for j, f in enumerate(frame_ids):
-                engine.frame(("f", f), sts_w[j], sts_r[j], scene_a, human_a, refined_a, gimgs[f % 8], accumulate=(j > 0),
-                             densify=stats)
-            engine.reduce()
+            cur = torch.cuda.current_stream(dev)
+            used = min(S, len(frame_ids))
+            for s_ in range(used):
+                st_ = lane_streams[s_]
+                st_.wait_stream(cur)
+                with torch.cuda.stream(st_):
+                    e = engines[s_]
+                    e.set_scene(scene_a)
+                    for j, idx in enumerate(range(s_, len(frame_ids), S)):
+                        f = frame_ids[idx]
+                        e.frame(("f", f), sts_w[idx], sts_r[idx], scene_a, human_a, refined_a, gimgs[f % 8],
+                                accumulate=(j > 0), densify=lane_stats[s_])
+                    e.reduce()
+            for s_ in range(used):
+                cur.wait_stream(lane_streams[s_])
+            for s_ in range(1, used):  # fold the lanes, fixed order
+                flat.add_(engines[s_].flat_bucket())
+                stats["grad_accum"].add_(lane_stats[s_]["grad_accum"])
+                stats["count"].add_(lane_stats[s_]["count"])
+                torch.maximum(stats["radius_max"], lane_stats[s_]["radius_max"], out=stats["radius_max"])
         return body
 
     body = body_for(weak_frames, st_w, st_r)
     graph, launches_per_step = (None, 0)
     if not args.no_graph:
         graph, launches_per_step = env.capture(body)
-
-    flat = engine.flat_bucket()  # ONE flat fp32 buffer: every per-Gaussian gradient of the three parameter sets
 
     def collectives():
         """one gradient all-reduce per step + the small densification-statistics reduction
@@ -500,7 +529,7 @@ def bench_five(env, args, wl, wl_key):
             torch.cuda.synchronize(dev)
         clocks.window = "timed region, then the same step replayed untimed until >= 20 NVML samples were taken"
     clk = clocks.stop() if clocks else None
-    if engine.overflowed():
+    if any(e.overflowed() for e in engines):
         raise SystemExit("bench.py: duplicate capacity overflowed; results invalid")
     launches = launches_eager if graph is None else K * launches_per_step
     fps = world * F * K / (ms_total * 1e-3)
@@ -572,8 +601,8 @@ def bench_five(env, args, wl, wl_key):
         e2e, e2e_eager = e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_a, max(caps.values()),
                                   collectives if world > 1 else None)
 
-    extra = {"cuda_graph": graph is not None, "dup_capacity": caps, "engine": engine_kind,
-             "streams": engine.describe()}
+    extra = {"cuda_graph": graph is not None, "dup_capacity": caps, "engine": engine_kind, "lanes": S,
+             "streams": engine.describe() + f"; {S} training frame(s) in flight"}
     return {"value": fps, "ms_per_step": ms_total / K, "clocks": clk, "launches": int(launches), "roofline": roofline,
             "e2e": e2e, "e2e_eager": e2e_eager, "strong_scaling": strong, "collective": coll, "wall": wall, "config": extra,
             "warmup": Wm}
@@ -598,7 +627,7 @@ def e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_
     h2d = nbytes(host) + F * 3 * N * 4
     d2h = nbytes(host_grads) + F * 4
     renderer = GaussianRenderer()
-    S = max(1, min(args.lanes, F))
+    S = max(1, min(4, F))  # frames in flight on the autograd path (each frame: five renders in sequence on its lane)
     cat = lambda a, b: {k: torch.cat((a[k].detach(), b[k])) for k in a}  # model.py:117-125
 
     def frame_loss(lv, f, tgt, use_cached_settings):
@@ -1061,6 +1090,7 @@ def run_b200(args):
 
     single = None
     if pattern == "five" and not args.no_single:  # continuity with round 1: BASELINE configs[1], one render per frame
+        args.lanes = args._lanes_user if args._lanes_user is not None else 4
         single = bench_single(env, args, WORKLOADS["C2"], "C2", brief=True)
 
     cpu = None

@@ -12,6 +12,7 @@ _PKG = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_PKG, "libb200raster.so")
 LIB_PATH = os.environ.get("B2R_LIB", LIB_PATH)  # tuning experiments: an alternative build of the same library
 
+ABI_VERSION = 3
 B2R_OK = 0
 B2R_FLAG_NO_TILE_CULL = 1
 B2R_FLAG_DEBUG = 2
@@ -45,6 +46,14 @@ class B2RWorkspace(C.Structure):
     _fields_ = [
         ("ctx", _fp), ("ctx_bytes", C.c_size_t), ("dup_ids", _fp), ("dup_capacity", C.c_uint64),
         ("scratch", _fp), ("scratch_bytes", C.c_size_t), ("status_mirror", _fp), ("status_token", C.c_uint64),
+        ("checkpoints", _fp), ("checkpoint_bytes", C.c_size_t),  # ABI v3: segment table + blend-state checkpoints
+    ]
+
+
+class B2RView(C.Structure):
+    _fields_ = [
+        ("id_begin", C.c_uint32), ("id_end", C.c_uint32), ("bg", _fp), ("final_T", _fp), ("n_contrib", _fp),
+        ("checkpoints", _fp), ("checkpoint_bytes", C.c_size_t), ("skip_below", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
@@ -60,11 +69,13 @@ class B2RBackwardArgs(C.Structure):
         ("flags", C.c_uint32), ("first_row", C.c_uint32),
         ("densify_grad_accum", _fp), ("densify_count", _fp), ("densify_radius_max", _fp),
         ("dL_dskin_xyz", _fp), ("dL_dskin_G", _fp),
+        ("dL_dposed", _fp),  # ABI v3 INPUT: gradient arriving at the posed positions (fused skinning)
+        ("densify_rows", C.c_uint32), ("reserved", C.c_uint32),
     ]
 
 
-# B2RStatus.consumed_fwd / consumed_bwd are sums over composite CTAs; four quarter-tile CTAs walk each tile's list
-CONSUMED_FWD_DIV = 4
+# B2RStatus.consumed_fwd / consumed_bwd: list entries staged per tile, x 8 (forward) / x 4 (backward) -- b200raster.h
+CONSUMED_FWD_DIV = 8
 CONSUMED_BWD_DIV = 4
 
 B2R_BWD_ACCUMULATE = 1
@@ -80,6 +91,14 @@ SYMBOLS = [
     ("b2r_ctx_bytes", C.c_size_t, [C.c_int32, C.c_int32, C.c_int32]),
     ("b2r_scratch_bytes", C.c_size_t, [C.c_int32, C.c_int32, C.c_int32, C.c_uint64]),
     ("b2r_backward_scratch_bytes", C.c_size_t, [C.c_int32]),
+    ("b2r_checkpoint_bytes", C.c_size_t, [C.c_int32, C.c_int32, C.c_uint64]),
+    ("b2r_forward_bin", C.c_int, [C.POINTER(B2RScene), C.POINTER(B2RWorkspace), _fp]),
+    ("b2r_forward_composite", C.c_int, [C.POINTER(B2RScene), C.POINTER(B2RWorkspace), C.POINTER(B2RView),
+                                        C.POINTER(B2RForwardOutputs), _fp]),
+    ("b2r_backward_composite", C.c_int, [C.POINTER(B2RScene), C.POINTER(B2RWorkspace), C.POINTER(B2RView),
+                                         C.POINTER(B2RBackwardArgs), _fp, C.c_size_t, _fp]),
+    ("b2r_backward_project", C.c_int, [C.POINTER(B2RScene), C.POINTER(B2RWorkspace), C.POINTER(B2RBackwardArgs), _fp,
+                                       C.c_size_t, _fp]),
     ("b2r_forward_project", C.c_int, [C.POINTER(B2RScene), C.POINTER(B2RWorkspace), _fp, _fp]),
     ("b2r_forward_render", C.c_int, [C.POINTER(B2RScene), C.POINTER(B2RWorkspace), C.POINTER(B2RForwardOutputs), _fp]),
     ("b2r_forward", C.c_int, [C.POINTER(B2RScene), C.POINTER(B2RWorkspace), C.POINTER(B2RForwardOutputs), _fp]),
@@ -114,9 +133,9 @@ def load():
         fn = getattr(lib, name)  # AttributeError if the .so is stale
         fn.restype = restype
         fn.argtypes = argtypes
-    if lib.b2r_abi_version() != 2:
+    if lib.b2r_abi_version() != ABI_VERSION:
         raise RuntimeError("b200raster: ABI version mismatch between the Python binding and libb200raster.so")
-    for idx, cls in enumerate((B2RScene, B2RStatus, B2RWorkspace, B2RForwardOutputs, B2RBackwardArgs)):
+    for idx, cls in enumerate((B2RScene, B2RStatus, B2RWorkspace, B2RForwardOutputs, B2RBackwardArgs, B2RView)):
         if lib.b2r_sizeof(idx) != C.sizeof(cls):
             raise RuntimeError(f"b200raster: struct layout drift for {cls.__name__}: "
                                f"{lib.b2r_sizeof(idx)} (C) vs {C.sizeof(cls)} (ctypes)")

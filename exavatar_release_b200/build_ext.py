@@ -21,6 +21,14 @@ NVCC_FLAGS = [
 ]
 
 
+# Per-file flags.  project.cu holds the DECISION path of the projection (near-plane cull, radius = ceil(3 sqrt(lambda)),
+# tile rect, pixel centre): compiled without fma contraction its arithmetic is, operation for operation, the oracle's C
+# expression order (SURVEY.md section 7.2 "bit-compatible discrete decisions"), so radii / rects / centres are identical
+# bit for bit instead of "equal except when 3 sqrt(lambda) lands within an ulp of an integer".  The kernel is
+# latency-bound; the ~100 extra FP instructions per Gaussian do not show in its duration.
+PER_FILE_FLAGS = {"project.cu": ["--fmad=false"]}
+
+
 def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
@@ -29,7 +37,8 @@ def _stale() -> bool:
     if not os.path.exists(LIB):
         return True
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(PKG, "..", "include", "b200raster.h")]
+    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(PKG, "..", "include", "b200raster.h"),
+                                                                  os.path.abspath(__file__)]
     return any(os.path.getmtime(d) > t for d in deps)
 
 
@@ -46,13 +55,15 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     flags = [f for f in NVCC_FLAGS if f != "--shared"]
     srcs = sources()
     objs = [os.path.join(objdir, os.path.basename(s)[:-3] + ".o") for s in srcs]
-    hdr_t = max(os.path.getmtime(d) for d in glob.glob(os.path.join(CSRC, "*.cuh")) + [os.path.join(PKG, "..", "include", "b200raster.h")])
+    hdr_t = max(os.path.getmtime(d) for d in glob.glob(os.path.join(CSRC, "*.cuh")) +
+                [os.path.join(PKG, "..", "include", "b200raster.h"), os.path.abspath(__file__)])  # flags live in this file
 
     def compile_one(pair):
         src, obj = pair
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(src), hdr_t) and not extra:
             return
-        cmd = [nvcc, *flags, *extra, *(["-Xptxas", "-v"] if ptxas_info else []), "-c", "-o", obj, src]
+        cmd = [nvcc, *flags, *PER_FILE_FLAGS.get(os.path.basename(src), []), *extra,
+               *(["-Xptxas", "-v"] if ptxas_info else []), "-c", "-o", obj, src]
         if verbose:
             print(" ".join(cmd), flush=True)
         subprocess.check_call(cmd)

@@ -43,6 +43,7 @@ int validate_ws(const B2RScene* sc, const B2RWorkspace* ws, bool need_scratch) {
     if (ws->scratch_bytes < b2r_scratch_bytes(sc->P, sc->width, sc->height, ws->dup_capacity)) return B2R_E_WORKSPACE;
   }
   if (ws->dup_capacity > 0 && !ws->dup_ids) return B2R_E_INVALID;
+  if (ws->checkpoints && ws->checkpoint_bytes < b2r_checkpoint_bytes(sc->width, sc->height, ws->dup_capacity)) return B2R_E_WORKSPACE;
   return B2R_OK;
 }
 
@@ -72,6 +73,7 @@ size_t b2r_sizeof(int which) {
     case 2: return sizeof(B2RWorkspace);
     case 3: return sizeof(B2RForwardOutputs);
     case 4: return sizeof(B2RBackwardArgs);
+    case 5: return sizeof(B2RView);
     default: return 0;
   }
 }
@@ -83,6 +85,12 @@ size_t b2r_scratch_bytes(int32_t P, int32_t width, int32_t height, uint64_t dup_
 }
 
 size_t b2r_backward_scratch_bytes(int32_t P) { return align_up((size_t)(P > 0 ? P : 1) * 12 * sizeof(float)); }
+
+size_t b2r_checkpoint_bytes(int32_t width, int32_t height, uint64_t dup_capacity) {
+  const CtxLayout L = ctx_layout(0, width, height);
+  const uint32_t ms = max_segments(L.tiles, dup_capacity);
+  return seg_table_bytes(ms) + (size_t)ms * CK_REC_BYTES;
+}
 
 int b2r_forward_project(const B2RScene* scene, const B2RWorkspace* ws, int32_t* radii, void* stream) {
   int rc = validate_scene(scene);
@@ -103,6 +111,47 @@ static int forward_render(const B2RScene* scene, const B2RWorkspace* ws, const B
   if (!out || !out->color || !out->depth || !out->alpha) return B2R_E_INVALID;
   const Ctx cx = resolve(ws, scene->P, scene->width, scene->height);
   rc = launch_binning(*scene, cx, rescan, (cudaStream_t)stream);
+  if (rc) return rc;
+  return launch_composite_fwd(*scene, cx, *out, (cudaStream_t)stream);
+}
+
+// a view narrows the Gaussian range, swaps the background and redirects the per-pixel state / checkpoint records
+static int apply_view(Ctx& cx, const B2RScene* scene, const B2RWorkspace* ws, const B2RView* v) {
+  if (!v) return B2R_OK;
+  if (v->id_end < v->id_begin || (int64_t)v->id_end > (int64_t)scene->P) return B2R_E_INVALID;
+  if ((v->final_T != nullptr) != (v->n_contrib != nullptr)) return B2R_E_INVALID;
+  cx.id_begin = v->id_begin;
+  cx.id_span = v->id_end - v->id_begin;
+  cx.bg = v->bg;
+  cx.skip_below = v->skip_below;
+  if (v->final_T) { cx.final_T = v->final_T; cx.n_contrib = v->n_contrib; }
+  if (v->checkpoints && cx.ckpt) {  // records only; the segment table is the workspace's (one per binned scene)
+    const size_t need = seg_table_bytes(cx.max_segs) + (size_t)cx.max_segs * CK_REC_BYTES;
+    if (v->checkpoint_bytes < need) return B2R_E_WORKSPACE;
+    cx.ckpt = (float*)((char*)v->checkpoints + seg_table_bytes(cx.max_segs));
+  }
+  (void)ws;
+  return B2R_OK;
+}
+
+int b2r_forward_bin(const B2RScene* scene, const B2RWorkspace* ws, void* stream) {
+  int rc = validate_scene(scene);
+  if (rc) return rc;
+  rc = validate_ws(scene, ws, true);
+  if (rc) return rc;
+  const Ctx cx = resolve(ws, scene->P, scene->width, scene->height);
+  return launch_binning(*scene, cx, false, (cudaStream_t)stream);
+}
+
+int b2r_forward_composite(const B2RScene* scene, const B2RWorkspace* ws, const B2RView* view,
+                          const B2RForwardOutputs* out, void* stream) {
+  int rc = validate_scene(scene);
+  if (rc) return rc;
+  rc = validate_ws(scene, ws, false);
+  if (rc) return rc;
+  if (!out || !out->color || !out->depth || !out->alpha) return B2R_E_INVALID;
+  Ctx cx = resolve(ws, scene->P, scene->width, scene->height);
+  rc = apply_view(cx, scene, ws, view);
   if (rc) return rc;
   return launch_composite_fwd(*scene, cx, *out, (cudaStream_t)stream);
 }
@@ -128,11 +177,42 @@ int b2r_backward(const B2RScene* scene, const B2RWorkspace* ws, const B2RBackwar
   if (bwd_scratch_bytes < b2r_backward_scratch_bytes(scene->P)) return B2R_E_WORKSPACE;
   if (scene->shs && args->dL_dshs == nullptr && scene->P > 0) return B2R_E_INVALID;
   if ((int64_t)args->first_row > (int64_t)scene->P) return B2R_E_INVALID;
+  if (args->dL_dposed && !scene->skin_xyz) return B2R_E_INVALID;
   const Ctx cx = resolve(ws, scene->P, scene->width, scene->height);
   float* gacc = (float*)bwd_scratch;
   rc = launch_composite_bwd(*scene, cx, *args, gacc, (cudaStream_t)stream);
   if (rc) return rc;
   return launch_project_bwd(*scene, cx, *args, gacc, (cudaStream_t)stream);
+}
+
+int b2r_backward_composite(const B2RScene* scene, const B2RWorkspace* ws, const B2RView* view, const B2RBackwardArgs* args,
+                           void* bwd_scratch, size_t bwd_scratch_bytes, void* stream) {
+  int rc = validate_scene(scene);
+  if (rc) return rc;
+  rc = validate_ws(scene, ws, false);
+  if (rc) return rc;
+  if (!args || !args->dL_dcolor || !bwd_scratch) return B2R_E_INVALID;
+  if (bwd_scratch_bytes < b2r_backward_scratch_bytes(scene->P)) return B2R_E_WORKSPACE;
+  if ((int64_t)args->first_row > (int64_t)scene->P) return B2R_E_INVALID;
+  Ctx cx = resolve(ws, scene->P, scene->width, scene->height);
+  rc = apply_view(cx, scene, ws, view);
+  if (rc) return rc;
+  return launch_composite_bwd(*scene, cx, *args, (float*)bwd_scratch, (cudaStream_t)stream);
+}
+
+int b2r_backward_project(const B2RScene* scene, const B2RWorkspace* ws, const B2RBackwardArgs* args, void* bwd_scratch,
+                         size_t bwd_scratch_bytes, void* stream) {
+  int rc = validate_scene(scene);
+  if (rc) return rc;
+  rc = validate_ws(scene, ws, false);
+  if (rc) return rc;
+  if (!args || !bwd_scratch) return B2R_E_INVALID;
+  if (bwd_scratch_bytes < b2r_backward_scratch_bytes(scene->P)) return B2R_E_WORKSPACE;
+  if (scene->shs && args->dL_dshs == nullptr && scene->P > 0) return B2R_E_INVALID;
+  if ((int64_t)args->first_row > (int64_t)scene->P) return B2R_E_INVALID;
+  if (args->dL_dposed && !scene->skin_xyz) return B2R_E_INVALID;
+  const Ctx cx = resolve(ws, scene->P, scene->width, scene->height);
+  return launch_project_bwd(*scene, cx, *args, (const float*)bwd_scratch, (cudaStream_t)stream);
 }
 
 int b2r_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present, void* stream) {

@@ -168,8 +168,10 @@ struct RadixSmem {
 
 // PAIRS = false: dst[i] = id of the i-th entry in (depth, id) order.  PAIRS = true (one chunk of a long list): the sorted
 // (depth, id) pairs are written back over the chunk itself, to be merged with the other chunks by merge_chunks_kernel.
+// `maxid` (global, zeroed per render) receives the largest Gaussian index of the list (Ctx::tile_maxid).
 template <int CAP, int THREADS, bool PAIRS = false>
-__device__ __forceinline__ void radix_sort_tile(const uint2* src, uint32_t* dst, const int n, unsigned char* smem_raw) {
+__device__ __forceinline__ void radix_sort_tile(const uint2* src, uint32_t* dst, const int n, unsigned char* smem_raw,
+                                                uint32_t* maxid) {
   constexpr int W = THREADS / 32;
   uint32_t* keyA = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* keyB = keyA + CAP;
@@ -281,7 +283,14 @@ __device__ __forceinline__ void radix_sort_tile(const uint2* src, uint32_t* dst,
   }
   // ids of the sorted entries (kout is free now)
   uint32_t* ids = kout;
-  for (int i = tid; i < n; i += THREADS) ids[i] = src[iin[i]].y;
+  uint32_t vmax = 0u;
+  for (int i = tid; i < n; i += THREADS) {
+    const uint32_t id = src[iin[i]].y;
+    ids[i] = id;
+    vmax = max(vmax, id);
+  }
+  vmax = __reduce_max_sync(0xffffffffu, vmax);
+  if (lane == 0 && vmax) atomicMax(maxid, vmax);
   __syncthreads();
   // equal depths: ascending id (odd-even transposition restricted to runs of identical keys)
   for (;;) {
@@ -317,12 +326,14 @@ constexpr int WSORT_CAP = 512;
 constexpr size_t WSORT_BYTES = (size_t)WSORT_CAP * 12 + 256 * 2;  // keyA, keyB (u32), idxA, idxB (u16), hist (u16)
 
 __device__ __forceinline__ void warp_sort_tile(const uint2* __restrict__ src, uint32_t* __restrict__ dst, const int n,
-                                               unsigned char* smem_warp) {
+                                               unsigned char* smem_warp, uint32_t* __restrict__ maxid) {
   const int lane = threadIdx.x & 31;
   const unsigned below_mask = (1u << lane) - 1u;
   if (n <= 0) return;
   if (n <= 32) {  // rank sort in registers: position = number of entries with a smaller (depth, id)
     const uint2 kv = lane < n ? src[lane] : make_uint2(0xffffffffu, 0xffffffffu);
+    const uint32_t m = __reduce_max_sync(0xffffffffu, lane < n ? kv.y : 0u);
+    if (lane == 0) *maxid = m;
     const unsigned long long me = ((unsigned long long)kv.x << 32) | kv.y;
     int rank = 0;
     for (int j = 0; j < n; j++) {
@@ -400,7 +411,14 @@ __device__ __forceinline__ void warp_sort_tile(const uint2* __restrict__ src, ui
     { uint16_t* t = iin; iin = iout; iout = t; }
   }
   uint32_t* ids = kout;  // free now
-  for (int i = lane; i < n; i += 32) ids[i] = src[iin[i]].y;
+  uint32_t vmax = 0u;
+  for (int i = lane; i < n; i += 32) {
+    const uint32_t id = src[iin[i]].y;
+    ids[i] = id;
+    vmax = max(vmax, id);
+  }
+  vmax = __reduce_max_sync(0xffffffffu, vmax);
+  if (lane == 0) *maxid = vmax;
   __syncwarp();
   // equal depths: ascending id (odd-even transposition restricted to runs of identical keys)
   for (;;) {
@@ -447,20 +465,23 @@ __global__ void __launch_bounds__(THREADS) sort_mixed_kernel(const Ctx cx) {
         const int mid = (lo + hi + 1) >> 1;
         if ((int)cx.chunk_start[mid] <= b) lo = mid; else hi = mid - 1;
       }
-      const uint2 r = cx.ranges[cx.tile_order[lo]];
+      const uint32_t tile = cx.tile_order[lo];
+      const uint2 r = cx.ranges[tile];
       const int off = (b - (int)cx.chunk_start[lo]) * SORT_CHUNK;
       const int len = min(SORT_CHUNK, (int)(r.y - r.x) - off);
-      if (len > 1) radix_sort_tile<CAP, THREADS, true>(cx.keys + r.x + off, nullptr, len, smem_raw);
+      if (len > 1) radix_sort_tile<CAP, THREADS, true>(cx.keys + r.x + off, nullptr, len, smem_raw, cx.tile_maxid + tile);
+      else if (len == 1 && threadIdx.x == 0) atomicMax(cx.tile_maxid + tile, cx.keys[r.x + off].y);
       last_n = len;
     } else if (b < n_chunks + n_cta) {
-      const uint2 r = cx.ranges[cx.tile_order[n_large + (b - n_chunks)]];
+      const uint32_t tile = cx.tile_order[n_large + (b - n_chunks)];
+      const uint2 r = cx.ranges[tile];
       const int n = (int)(r.y - r.x);  // < 2048; can be below 512 when the duplicate capacity clamped the range
       const uint2* src = cx.keys + r.x;
       uint32_t* dst = cx.dup_ids + r.x;
       if (n > 32) {
-        radix_sort_tile<CAP, THREADS>(src, dst, n, smem_raw);
+        radix_sort_tile<CAP, THREADS>(src, dst, n, smem_raw, cx.tile_maxid + tile);
       } else {
-        if (threadIdx.x < 32) warp_sort_tile(src, dst, n, smem_raw);
+        if (threadIdx.x < 32) warp_sort_tile(src, dst, n, smem_raw, cx.tile_maxid + tile);
         __syncthreads();
       }
       last_n = n;
@@ -468,9 +489,11 @@ __global__ void __launch_bounds__(THREADS) sort_mixed_kernel(const Ctx cx) {
       const int warp = threadIdx.x >> 5;
       const int t = n_ge512 + (b - n_chunks - n_cta) * (THREADS / 32) + warp;
       if (t < cx.tiles) {
-        const uint2 r = cx.ranges[cx.tile_order[t]];
+        const uint32_t tile = cx.tile_order[t];
+        const uint2 r = cx.ranges[tile];
         last_n = -(int)(r.y - r.x);
-        warp_sort_tile(cx.keys + r.x, cx.dup_ids + r.x, (int)(r.y - r.x), smem_raw + (size_t)warp * WSORT_BYTES);
+        warp_sort_tile(cx.keys + r.x, cx.dup_ids + r.x, (int)(r.y - r.x), smem_raw + (size_t)warp * WSORT_BYTES,
+                       cx.tile_maxid + tile);
       }
     }
   }

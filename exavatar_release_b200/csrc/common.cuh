@@ -26,6 +26,23 @@ constexpr float INV_LOG2E = 0.6931471805599453f;
 constexpr float CULL_MARGIN2 = 0.02f;
 
 constexpr int SORT_CHUNK = 2048;  // per-tile sort: lists are sorted in chunks of this many entries (binning.cu)
+// Segmented composites (composite_fwd4.cu / composite_bwd4.cu).  A tile's depth-sorted list is cut every SEG entries;
+// the forward stores the per-pixel blend state at every cut (a "checkpoint record"), which lets the backward replay
+// each (quarter tile, segment) as an independent work item, and lists of >= HEAVY_MIN entries are blended by eight
+// warps per 8x4 pixel rect in the forward.  SEG is also the forward's staging batch, so cuts are batch boundaries.
+constexpr int SEG = 256;
+constexpr int HEAVY_MIN = 512;
+constexpr int CK_PLANE0 = TILE_PIX * 4;              // floats: per pixel (T, C_r, C_g, C_b)
+constexpr int CK_REC_FLOATS = TILE_PIX * 4 + TILE_PIX * 2;  // + per pixel (depth sum, alpha sum)
+constexpr size_t CK_REC_BYTES = (size_t)CK_REC_FLOATS * 4;  // 6144
+// slots of Ctx::classes (written by tile_scan_kernel; positions refer to tile_order, which is sorted longest first)
+enum { CLS_N_LARGE = 0,   // tiles with >= 2048 entries (sorted in chunks)
+       CLS_N_GE512 = 1,   // tiles with >= 512 entries  (CTA-class sort; "heavy" tiles of the forward composite)
+       CLS_N_MULTI = 2,   // tiles cut into segments (>= 256 entries), 0 when the caller gave no checkpoint buffer
+       CLS_N_CHUNKS = 3,  // sort chunks of the large tiles
+       CLS_TOTAL_SEGS = 4,  // segments of the multi-segment tiles
+       CLS_N_GE1024 = 5,    // tiles with >= 1024 entries (alternative heavy threshold of the forward composite)
+       CLS_COUNT = 8 };
 constexpr size_t ALIGN = 256;
 __host__ __device__ inline size_t align_up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }
 
@@ -37,7 +54,8 @@ struct Geom {  // 48 bytes per Gaussian, three 16-byte vectors
 static_assert(sizeof(Geom) == 48, "Geom must be 48 bytes");
 
 struct CtxLayout {
-  size_t status, geom, aux, ranges, tile_count, tile_cursor, tile_order, chunk_start, final_T, n_contrib, total;
+  size_t status, geom, aux, ranges, tile_count, tile_cursor, tile_order, chunk_start, seg_start, classes, tile_maxid,
+      final_T, n_contrib, total;
   int gx, gy, tiles;
 };
 __host__ __device__ inline CtxLayout ctx_layout(int P, int W, int H) {
@@ -55,6 +73,9 @@ __host__ __device__ inline CtxLayout ctx_layout(int P, int W, int H) {
   L.tile_cursor = o; o += align_up((size_t)L.tiles * 4);
   L.tile_order = o; o += align_up((size_t)L.tiles * 4);
   L.chunk_start = o; o += align_up((size_t)L.tiles * 4);
+  L.seg_start = o; o += align_up((size_t)L.tiles * 4);
+  L.classes = o; o += align_up((size_t)CLS_COUNT * 4);
+  L.tile_maxid = o; o += align_up((size_t)L.tiles * 4);
   L.final_T = o; o += align_up(N * 4);
   L.n_contrib = o; o += align_up(N * 4);
   L.total = o;
@@ -91,7 +112,22 @@ struct Ctx {
   uint64_t* status_mirror;
   uint64_t status_token;
   int gx, gy, tiles;
+  // segmentation (all null / 0 when the workspace carries no checkpoint buffer: every list is then one segment)
+  uint32_t* seg_start;   // by position in tile_order, multi-segment tiles: segments (= checkpoint records) of all earlier ones
+  uint32_t* classes;     // CLS_* counters
+  uint2* seg_table;      // one (tile_order position, segment index) per segment of the multi-segment tiles
+  float* ckpt;           // checkpoint records, CK_REC_FLOATS each
+  uint32_t max_segs;     // capacity of seg_table / ckpt in segments
+  // view (B2RView): which Gaussians take part, with which background, and where the per-pixel state lives
+  uint32_t id_begin, id_span;  // Gaussian i takes part iff i - id_begin < id_span (unsigned)
+  const float* bg;
+  uint32_t* tile_maxid;  // per tile: largest Gaussian index in its list (written by the per-tile sort)
+  uint32_t skip_below;   // != 0: the composites skip tiles whose tile_maxid < skip_below (B2RView.skip_below)
 };
+
+// capacity of the segment table / checkpoint store for a given duplicate capacity
+__host__ __device__ inline uint32_t max_segments(int tiles, uint64_t cap) { return (uint32_t)(cap / SEG) + (uint32_t)tiles; }
+__host__ __device__ inline size_t seg_table_bytes(uint32_t max_segs) { return align_up((size_t)max_segs * 8); }
 
 inline Ctx resolve(const B2RWorkspace* ws, int P, int W, int H) {
   CtxLayout L = ctx_layout(P, W, H);
@@ -115,6 +151,21 @@ inline Ctx resolve(const B2RWorkspace* ws, int P, int W, int H) {
   x.status_mirror = ws->status_mirror;
   x.status_token = ws->status_token;
   x.gx = L.gx; x.gy = L.gy; x.tiles = L.tiles;
+  x.seg_start = (uint32_t*)(c + L.seg_start);
+  x.classes = (uint32_t*)(c + L.classes);
+  x.seg_table = nullptr; x.ckpt = nullptr; x.max_segs = 0;
+  if (ws->checkpoints) {
+    const uint32_t ms = max_segments(L.tiles, ws->dup_capacity);
+    if (ws->checkpoint_bytes >= seg_table_bytes(ms) + (size_t)ms * CK_REC_BYTES) {
+      x.seg_table = (uint2*)ws->checkpoints;
+      x.ckpt = (float*)((char*)ws->checkpoints + seg_table_bytes(ms));
+      x.max_segs = ms;
+    }
+  }
+  x.id_begin = 0; x.id_span = 0xffffffffu;
+  x.bg = nullptr;
+  x.tile_maxid = (uint32_t*)(c + L.tile_maxid);
+  x.skip_below = 0;
   return x;
 }
 
@@ -279,6 +330,7 @@ int launch_binning(const B2RScene& sc, const Ctx& cx, bool rescan, cudaStream_t 
 void launch_tile_scan(const Ctx& cx, cudaStream_t st);
 int launch_composite_fwd(const B2RScene& sc, const Ctx& cx, const B2RForwardOutputs& out, cudaStream_t st);
 int launch_composite_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, float* gacc, cudaStream_t st);
+
 int launch_project_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, const float* gacc, cudaStream_t st);
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t st);
 

@@ -106,8 +106,14 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
     }
     const float3 pv = xform4x3(p, cam.v);
     if (pv.z > K_NEAR) {  // App. A.1 step 1
-      const float4 ph = xform4x4(p, cam.p);
-      const float pw = 1.f / (ph.w + K_EPS_W);
+      // Homogeneous position and pixel centre WITHOUT fma contraction, operation for operation as the oracle's C
+      // expression (App. A.1 steps 2, 7).  One ulp of a pixel coordinate near 1000 is 6e-5 px; through a sharp splat's
+      // exponent that is a 1e-4 relative change of alpha, enough to flip alpha >= 1/255 decisions the oracle's threshold
+      // margins do not expect (seen at 1024^2 / 1080p, profiles/r02_notes.md).  Bit-identical centres remove that source.
+      const float ph_x = dot4_rn(cam.p[0], p.x, cam.p[4], p.y, cam.p[8], p.z, cam.p[12]);
+      const float ph_y = dot4_rn(cam.p[1], p.x, cam.p[5], p.y, cam.p[9], p.z, cam.p[13]);
+      const float ph_w = dot4_rn(cam.p[3], p.x, cam.p[7], p.y, cam.p[11], p.z, cam.p[15]);
+      const float pw = __fdiv_rn(1.f, __fadd_rn(ph_w, K_EPS_W));
       float c6[6];
       if (sc.cov3D_precomp) {
 #pragma unroll
@@ -129,8 +135,8 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
         const float root = sqrtf(fmaxf(K_EIG_FLOOR, mid * mid - det));
         const float lam = fmaxf(mid + root, mid - root);
         const int radius = (int)ceilf(3.f * sqrtf(lam));
-        const float px = ((ph.x * pw + 1.f) * (float)cam.W - 1.f) * 0.5f;
-        const float py = ((ph.y * pw + 1.f) * (float)cam.H - 1.f) * 0.5f;
+        const float px = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(ph_x, pw), 1.f), (float)cam.W), -1.f), 0.5f);
+        const float py = __fmul_rn(__fadd_rn(__fmul_rn(__fadd_rn(__fmul_rn(ph_y, pw), 1.f), (float)cam.H), -1.f), 0.5f);
         int x0 = (int)((px - (float)radius) / (float)TILE), y0 = (int)((py - (float)radius) / (float)TILE);
         int x1 = (int)((px + (float)radius + (float)(TILE - 1)) / (float)TILE);
         int y1 = (int)((py + (float)radius + (float)(TILE - 1)) / (float)TILE);
@@ -234,7 +240,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx) {
   // by floor(log2(n)) descending.  Tile cost is ~linear in n and spans three orders of magnitude, so launching in
   // index order leaves most SMs idle behind a few heavy tiles that happened to start late.
   __shared__ uint32_t bin_cursor[34];
-  __shared__ uint32_t n_large_s;
+  __shared__ uint32_t n_large_s, n_multi_s;
   if (threadIdx.x < 34) bin_cursor[threadIdx.x] = 0;
   __syncthreads();
   auto bin_of = [](uint32_t n) { return n == 0 ? 33 : __clz(n); };  // clz = 31 - floor(log2 n): small bin = long list
@@ -250,6 +256,12 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx) {
     // class boundaries of the per-tile sort (binning.cu): bins 0..20 hold n >= 2048, bins 0..22 hold n >= 512
     cx.status->reserved[0] = (unsigned long long)bin_cursor[21] | ((unsigned long long)bin_cursor[23] << 32);
     n_large_s = bin_cursor[21];
+    // segmented composites: tiles of >= SEG (256) entries are the bins 0..23; cut only when there is room for checkpoints
+    n_multi_s = cx.ckpt ? bin_cursor[24] : 0u;
+    cx.classes[CLS_N_LARGE] = bin_cursor[21];
+    cx.classes[CLS_N_GE512] = bin_cursor[23];
+    cx.classes[CLS_N_GE1024] = bin_cursor[22];
+    cx.classes[CLS_N_MULTI] = n_multi_s;
   }
   __syncthreads();
   for (int t = threadIdx.x; t < cx.tiles; t += blockDim.x) {
@@ -278,7 +290,41 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx) {
       if (t < n_large) cx.chunk_start[t] = run + incl - c;
       run += __shfl_sync(0xffffffffu, incl, 31);
     }
-    if (lane == 0) cx.status->reserved[1] = run;
+    if (lane == 0) {
+      cx.status->reserved[1] = run;
+      cx.classes[CLS_N_CHUNKS] = run;
+    }
+    // Segment table of the multi-segment tiles (composite_fwd4.cu / composite_bwd4.cu): seg_start[t] = segments of all
+    // earlier such tiles = index of the tile's first checkpoint record.
+    const uint32_t n_multi = n_multi_s;
+    uint32_t segs = 0;
+    for (uint32_t base = 0; base < n_multi; base += 32) {
+      const uint32_t t = base + lane;
+      uint32_t c = 0;
+      if (t < n_multi) {
+        const uint2 r = cx.ranges[cx.tile_order[t]];
+        c = (r.y - r.x + SEG - 1) / SEG;
+      }
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      if (t < n_multi) cx.seg_start[t] = segs + incl - c;
+      segs += __shfl_sync(0xffffffffu, incl, 31);
+    }
+    if (lane == 0) {
+      // cannot exceed the store by construction (sum of ceil(n / 256) <= capacity / 256 + tiles); guard all the same
+      if (segs > cx.max_segs) { segs = 0; cx.classes[CLS_N_MULTI] = 0; n_multi_s = 0; }
+      cx.classes[CLS_TOTAL_SEGS] = segs;
+    }
+  }
+  __syncthreads();
+  for (uint32_t t = threadIdx.x; t < n_multi_s; t += blockDim.x) {  // one (tile, segment) entry per backward work item
+    const uint2 r = cx.ranges[cx.tile_order[t]];
+    const uint32_t c = (r.y - r.x + SEG - 1) / SEG, s0 = cx.seg_start[t];
+    for (uint32_t k = 0; k < c; k++) cx.seg_table[s0 + k] = make_uint2(t, k);
   }
   if (threadIdx.x == 0) {
     const uint64_t total = carry_s;
@@ -298,7 +344,10 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx) {
 // resets the status block and the per-tile counters the projection kernel accumulates into
 __global__ void status_reset_kernel(const Ctx cx) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (t < cx.tiles) cx.tile_count[t] = 0u;
+  if (t < cx.tiles) {
+    cx.tile_count[t] = 0u;
+    cx.tile_maxid[t] = 0u;
+  }
   if (t == 0) {
     B2RStatus* s = cx.status;
     s->num_dups = 0;

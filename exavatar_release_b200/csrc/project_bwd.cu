@@ -27,6 +27,10 @@ __device__ __forceinline__ void project_bwd_one(const B2RScene& sc, const Ctx& c
   float3 p = make_float3(0.f, 0.f, 0.f);
   Cam cam;
   Skin skin;
+  // gradient arriving at the posed position itself (other ExAvatar modules read it, model.py:172-173): also for
+  // Gaussians this render culled
+  const bool posed_in = wrow != nullptr && out.dL_dposed != nullptr;
+  if (posed_in && !visible) skin = skin_position(sc, i, wrow);
 
   if (visible) {
     cam = load_cam(sc);
@@ -209,9 +213,15 @@ __device__ __forceinline__ void project_bwd_one(const B2RScene& sc, const Ctx& c
     }
   }
 
-  if (visible && out.densify_grad_accum) out.densify_grad_accum[oi] += sqrtf(dm2[0] * dm2[0] + dm2[1] * dm2[1]);
-  if (visible && out.densify_count) out.densify_count[oi] += 1.f;
-  if (visible && out.densify_radius_max) out.densify_radius_max[oi] = fmaxf(out.densify_radius_max[oi], (float)aux.z);
+  if (posed_in) {
+    dm[0] += __ldg(out.dL_dposed + 3 * (size_t)i);
+    dm[1] += __ldg(out.dL_dposed + 3 * (size_t)i + 1);
+    dm[2] += __ldg(out.dL_dposed + 3 * (size_t)i + 2);
+  }
+  const bool track = visible && (out.densify_rows == 0u || (uint32_t)i < out.densify_rows);
+  if (track && out.densify_grad_accum) out.densify_grad_accum[oi] += sqrtf(dm2[0] * dm2[0] + dm2[1] * dm2[1]);
+  if (track && out.densify_count) out.densify_count[oi] += 1.f;
+  if (track && out.densify_radius_max) out.densify_radius_max[oi] = fmaxf(out.densify_radius_max[oi], (float)aux.z);
   auto put3 = [&](float* base, const float* v) {
     if (!base) return;
     float* d = base + 3 * oi;
@@ -222,7 +232,7 @@ __device__ __forceinline__ void project_bwd_one(const B2RScene& sc, const Ctx& c
   if (wrow && (out.dL_dskin_xyz || out.dL_dskin_G)) {
     float gc[3] = {dm[0], dm[1], dm[2]}, dx[3] = {0.f, 0.f, 0.f}, G[12];
     float xs[4] = {0.f, 0.f, 0.f, 0.f};
-    if (visible) {
+    if (visible || posed_in) {
       if (sc.skin_cam_Rinv) {  // g_cam = Rinv^T g_world
         const float* R = sc.skin_cam_Rinv;
         gc[0] = __ldg(R) * dm[0] + __ldg(R + 3) * dm[1] + __ldg(R + 6) * dm[2];
@@ -287,7 +297,8 @@ __global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, con
   // out.first_row: Gaussians below it are a detached prefix (ExAvatar renders cat(scene.detach(), human),
   // model.py:117-125): nothing is written for them and Gaussian i lands in output row i - first_row
   const int first_row = (int)out.first_row;
-  const bool active = in_range && i >= first_row && !(accumulate && !visible);  // an invisible Gaussian has nothing to add
+  // an invisible Gaussian has nothing to add -- unless a gradient arrives at its posed position
+  const bool active = in_range && i >= first_row && !(accumulate && !visible && out.dL_dposed == nullptr);
   const bool use_sh = sc.shs != nullptr && out.dL_dshs != nullptr;
   const int L = sc.sh_coeffs * 3, S = L | 1;
   float* wstage = sh_stage + (size_t)warp * 32 * S;

@@ -13,6 +13,7 @@ bucket that is all-reduced once per step.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Dict, Optional
 
 import torch
@@ -22,7 +23,8 @@ from .rasterizer import _f32c, _make_scene, _ptr
 
 
 class FramePlan:
-    def __init__(self, P: int, width: int, height: int, dup_capacity: int, device, sh_coeffs: int = 0):
+    def __init__(self, P: int, width: int, height: int, dup_capacity: int, device, sh_coeffs: int = 0,
+                 segmented: bool = True):
         self.lib = L.load()
         self.P, self.W, self.H, self.M = int(P), int(width), int(height), int(sh_coeffs)
         self.device = torch.device(device)
@@ -39,8 +41,14 @@ class FramePlan:
         self.bwd_bytes = self.lib.b2r_backward_scratch_bytes(P)
         # zero once: every backward leaves it zero again (B2R_BWD_SCRATCH_ZEROED), so no memset node per render
         self.bwd_scratch = torch.zeros(self.bwd_bytes, dtype=torch.uint8, device=dev)
+        # segment table + blend-state checkpoints of the forward composite (lets the backward replay 256-entry list
+        # segments as independent work items); `segmented=False` reproduces the round-1 whole-list backward
+        segmented = segmented and os.environ.get("B2R_SEGMENTED", "1") != "0"  # A/B switch for measurements
+        self.ckpt_bytes = self.lib.b2r_checkpoint_bytes(width, height, self.capacity) if segmented else 0
+        self.ckpt = torch.empty(max(self.ckpt_bytes, 1), dtype=torch.uint8, device=dev) if segmented else None
         self.ws = L.B2RWorkspace(self.ctx_buf.data_ptr(), self.ctx_bytes, self.ids.data_ptr(), self.capacity,
-                                 self.scratch.data_ptr(), self.scratch_bytes, None, 0)
+                                 self.scratch.data_ptr(), self.scratch_bytes, None, 0,
+                                 self.ckpt.data_ptr() if segmented else None, self.ckpt_bytes)
         self.out = L.B2RForwardOutputs(self.color.data_ptr(), self.depth.data_ptr(), self.alpha.data_ptr(),
                                        self.radii.data_ptr())
         self._scenes = {}
@@ -263,6 +271,10 @@ class FiveRenderPlan:
         self.flat["human_refined"].add_(self.flat["scene_human_refined"])
         return self.flat["scene"], self.flat["human"], self.flat["human_refined"]
 
+    def grads(self, which: str) -> Dict[str, torch.Tensor]:
+        """Named gradient tensors of one parameter set ("scene" | "human" | "human_refined"), valid after reduce()."""
+        return dict(self.views[which])
+
     def flat_bucket(self) -> torch.Tensor:
         return self.all_flat[: self._reduced]
 
@@ -276,3 +288,199 @@ class FiveRenderPlan:
 
     def overflowed(self) -> bool:
         return any(p.status()["overflow"] for p in self.plans.values())
+
+
+class _Pass:
+    """One projection + binning of cat(scene, X) and the views composited from it (MergedFivePlan)."""
+
+    def __init__(self, lib, P, W, H, cap, n_views, device):
+        dev = device
+        self.P, self.cap = P, int(cap)
+        self.ctx_bytes = lib.b2r_ctx_bytes(P, W, H)
+        self.ctx_buf = torch.empty(self.ctx_bytes, dtype=torch.uint8, device=dev)
+        self.ids = torch.empty(max(self.cap, 1), dtype=torch.int32, device=dev)
+        self.scratch_bytes = lib.b2r_scratch_bytes(P, W, H, self.cap)
+        self.scratch = torch.empty(self.scratch_bytes, dtype=torch.uint8, device=dev)
+        self.bwd_bytes = lib.b2r_backward_scratch_bytes(P)
+        self.bwd_scratch = torch.zeros(self.bwd_bytes, dtype=torch.uint8, device=dev)  # stays zero across renders
+        self.ck_bytes = lib.b2r_checkpoint_bytes(W, H, self.cap)
+        self.ck = [torch.empty(self.ck_bytes, dtype=torch.uint8, device=dev) for _ in range(n_views)]
+        self.radii = torch.empty(P, dtype=torch.int32, device=dev)
+        self.ws = L.B2RWorkspace(self.ctx_buf.data_ptr(), self.ctx_bytes, self.ids.data_ptr(), self.cap,
+                                 self.scratch.data_ptr(), self.scratch_bytes, None, 0, self.ck[0].data_ptr(), self.ck_bytes)
+        f = lambda *s: torch.empty(s, dtype=torch.float32, device=dev)
+        self.img = [(f(3, H, W), f(1, H, W), f(1, H, W)) for _ in range(n_views)]
+        self.state = [(f(H * W), torch.empty(H * W, dtype=torch.int32, device=dev)) for _ in range(n_views)]
+        widths = {"mean_3d": 3, "opacity": 1, "scale": 3, "rotation": 4, "rgb": 3}
+        self.cat = {k: f(P, w) for k, w in widths.items()}
+        self.streams = [torch.cuda.Stream(dev) for _ in range(n_views)]
+
+    def status(self) -> dict:
+        raw = self.ctx_buf[: C.sizeof(L.B2RStatus)].cpu().numpy().tobytes()
+        s = L.B2RStatus.from_buffer_copy(raw)
+        return {"num_dups": int(s.num_dups), "overflow": int(s.overflow), "consumed_fwd": int(s.consumed_fwd),
+                "consumed_bwd": int(s.consumed_bwd)}
+
+
+class MergedFivePlan:
+    """ExAvatar's five renders per training frame (avatar/main/model.py:81-162) from TWO projection + binning passes
+    instead of five (kernel half):
+
+        pass A  Gaussians cat(scene, human)          views  scene-only | human-only (random bg) | both
+        pass B  Gaussians cat(scene, human_refined)  views               human-only (random bg) | both
+
+    The five renders share one camera, so the scene Gaussians project, bin and depth-sort identically in renders 1, 3, 5
+    and the human Gaussians in 2, 3 (refined: 4, 5).  A view (B2RView) composites the merged per-tile lists keeping only
+    one index range -- entries of the other population are dropped when a batch is staged -- with its own background and
+    per-pixel state.  Backward: the views of a pass accumulate their screen-space gradients into ONE scratch (the
+    combined view skips the detached scene prefix, `first_row`), and the backward projection runs once per pass: scene
+    rows carry the scene render's gradient, human rows the sum of the human-only and the combined render's -- what
+    `loss.backward()` leaves in the leaves of model.py:117-125.  Same results as five separate renders (tests/), 2/5 of
+    the projection / scatter / sort work.  Interface of FiveRenderPlan."""
+    PER = FiveRenderPlan.PER
+    VIEWS = {"A": ("scene", "human", "scene_human"), "B": ("human_refined", "scene_human_refined")}
+    SKIP = os.environ.get("B2R_SKIP_TILES", "1") != "0"  # A/B switch of the skipped human-free tiles
+
+    def __init__(self, P_scene: int, P_human: int, width: int, height: int, caps: Optional[Dict[str, int]], device):
+        self.lib = L.load()
+        self.Ps, self.Ph, self.P = int(P_scene), int(P_human), int(P_scene) + int(P_human)
+        self.W, self.H = int(width), int(height)
+        self.device = torch.device(device)
+        caps = caps or {"A": 8_000_000, "B": 8_000_000}
+        self.passes = {k: _Pass(self.lib, self.P, self.W, self.H, caps[k], len(v), self.device) for k, v in self.VIEWS.items()}
+        self.pass_streams = {k: torch.cuda.Stream(self.device) for k in self.passes}
+        # one flat gradient buffer: [pass A: scene rows | human rows][pass B: refined rows]
+        nA, nB = self.PER * self.P, self.PER * self.Ph
+        self.all_flat = torch.zeros(nA + nB, dtype=torch.float32, device=device)
+        _, self.views_A = _views_of(self.all_flat[:nA], self.P)
+        _, self.views_B = _views_of(self.all_flat[nA:], self.Ph)
+        Ps, P = self.Ps, self.P
+        self.ranges = {"scene": (0, Ps), "human": (Ps, P), "scene_human": (0, P), "human_refined": (Ps, P),
+                       "scene_human_refined": (0, P)}
+        self.first_row = {"scene": 0, "human": Ps, "scene_human": Ps, "human_refined": Ps, "scene_human_refined": Ps}
+        self._scenes = {}
+        self._keep = []
+
+    def describe(self) -> str:
+        return ("two merged passes per frame (cat(scene,human): 3 views; cat(scene,refined): 2 views), each one "
+                "projection + binning + sort; composites of a pass on parallel CUDA streams")
+
+    def set_scene(self, scene_assets: Dict[str, torch.Tensor]) -> None:
+        for ps in self.passes.values():
+            for k, buf in ps.cat.items():
+                buf[: self.Ps].copy_(scene_assets[k].reshape(self.Ps, -1))
+
+    def _scene_desc(self, key, ps, settings):
+        if key not in self._scenes:
+            sc, keep = _make_scene(settings, ps.cat["mean_3d"], None, ps.cat["rgb"], ps.cat["opacity"], ps.cat["scale"],
+                                   ps.cat["rotation"], None, 0)
+            self._scenes[key] = (sc, keep)
+        return self._scenes[key][0]
+
+    def _view(self, ps, v, name, bg):
+        lo, hi = self.ranges[name]
+        fT, nc = ps.state[v]
+        # combined views: tiles no human Gaussian reaches equal the scene-only view and carry no gradient -> skipped
+        skip = self.Ps if (self.SKIP and name in ("scene_human", "scene_human_refined")) else 0
+        return L.B2RView(lo, hi, _ptr(bg), fT.data_ptr(), nc.data_ptr(), ps.ck[v].data_ptr(), ps.ck_bytes, skip, 0)
+
+    def frame(self, key, settings, settings_human_bg, scene, human, refined, g_colors: Dict[str, torch.Tensor],
+              accumulate: bool, densify: Optional[Dict[str, torch.Tensor]] = None, serial: bool = False) -> None:
+        lib = self.lib
+        cur = torch.cuda.current_stream(self.device)
+        bg_h = _f32c(settings_human_bg.bg.to(self.device), "bg")
+        self._keep.append(bg_h)
+        del self._keep[:-64]
+        scene_img = self.passes["A"].img[0]  # the scene-only view: what the combined views equal away from the human
+        scene_done = torch.cuda.Event()
+        for pk, names in self.VIEWS.items():
+            ps = self.passes[pk]
+            st = cur if serial else self.pass_streams[pk]
+            if not serial:
+                st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                src = human if pk == "A" else refined
+                for k, buf in ps.cat.items():
+                    buf[self.Ps:].copy_(src[k].reshape(self.Ph, -1))
+                sc = self._scene_desc((key, pk), ps, settings)
+                sp = st.cuda_stream
+                L.check(lib.b2r_forward_project(C.byref(sc), C.byref(ps.ws), ps.radii.data_ptr(), sp), "b2r_forward_project")
+                L.check(lib.b2r_forward_bin(C.byref(sc), C.byref(ps.ws), sp), "b2r_forward_bin")
+                views = [self._view(ps, v, n, bg_h if n in ("human", "human_refined") else None) for v, n in enumerate(names)]
+                # forward + backward composite of every view; the views of a pass are independent of each other
+                for v, n in enumerate(names):
+                    vs = st if serial else ps.streams[v]
+                    if not serial:
+                        vs.wait_stream(st)
+                    with torch.cuda.stream(vs):
+                        color, depth, alpha = ps.img[v]
+                        if views[v].skip_below:  # pre-fill with the scene-only render; the composite overwrites human tiles
+                            vs.wait_event(scene_done)
+                            for dst, src in zip(ps.img[v], scene_img):
+                                dst.copy_(src)
+                        out = L.B2RForwardOutputs(color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), ps.radii.data_ptr())
+                        L.check(lib.b2r_forward_composite(C.byref(sc), C.byref(ps.ws), C.byref(views[v]), C.byref(out),
+                                                          vs.cuda_stream), "b2r_forward_composite")
+                        if n == "scene":
+                            scene_done.record(vs)
+                        a = L.B2RBackwardArgs(_ptr(g_colors[n]))
+                        a.flags = L.B2R_BWD_SCRATCH_ZEROED
+                        a.first_row = self.first_row[n]
+                        L.check(lib.b2r_backward_composite(C.byref(sc), C.byref(ps.ws), C.byref(views[v]), C.byref(a),
+                                                           ps.bwd_scratch.data_ptr(), ps.bwd_bytes, vs.cuda_stream),
+                                "b2r_backward_composite")
+                if not serial:
+                    for v in range(len(names)):
+                        st.wait_stream(ps.streams[v])
+                # one backward projection per pass
+                g = self.views_A if pk == "A" else self.views_B
+                a = L.B2RBackwardArgs(None, None, None, _ptr(g["means3D"]), _ptr(g["means2D"]), None, _ptr(g["colors"]),
+                                      _ptr(g["opacities"]), _ptr(g["scales"]), _ptr(g["rotations"]), None)
+                a.flags = (L.B2R_BWD_ACCUMULATE if accumulate else 0) | L.B2R_BWD_SCRATCH_ZEROED
+                a.first_row = 0 if pk == "A" else self.Ps
+                if pk == "A" and densify is not None:
+                    a.densify_grad_accum, a.densify_count = _ptr(densify.get("grad_accum")), _ptr(densify.get("count"))
+                    a.densify_radius_max = _ptr(densify.get("radius_max"))
+                    a.densify_rows = self.Ps
+                L.check(lib.b2r_backward_project(C.byref(sc), C.byref(ps.ws), C.byref(a), ps.bwd_scratch.data_ptr(),
+                                                 ps.bwd_bytes, sp), "b2r_backward_project")
+        if not serial:
+            for pk in self.passes:
+                cur.wait_stream(self.pass_streams[pk])
+
+    def render_outputs(self, render: str):
+        pk = "A" if render in self.VIEWS["A"] else "B"
+        ps = self.passes[pk]
+        color, _, alpha = ps.img[self.VIEWS[pk].index(render)]
+        lo, hi = self.ranges[render]
+        return color, alpha, ps.radii[lo:hi]
+
+    def reduce(self):
+        """(scene, human, human_refined) flat gradient buckets of the step.  Nothing to fold: the backward projection of
+        a pass already summed the renders that share a parameter set.  NOTE the buckets are row-interleaved views of the
+        pass buffers (means3D of all rows, then means2D ...); `grads(which)` gives named per-set tensors."""
+        return self.grads("scene"), self.grads("human"), self.grads("human_refined")
+
+    def grads(self, which: str) -> Dict[str, torch.Tensor]:
+        if which == "scene":
+            return {k: v[: self.Ps] for k, v in self.views_A.items()}
+        if which == "human":
+            return {k: v[self.Ps:] for k, v in self.views_A.items()}
+        return dict(self.views_B)
+
+    def flat_bucket(self) -> torch.Tensor:
+        return self.all_flat
+
+    def dups(self) -> Dict[str, int]:
+        return {k: ps.status()["num_dups"] for k, ps in self.passes.items()}
+
+    def consumed(self) -> Dict[str, list]:
+        fwd, bwd = [], []
+        for pk, names in self.VIEWS.items():  # the views of a pass add into the same counters: per-launch averages
+            s = self.passes[pk].status()
+            fwd += [s["consumed_fwd"] / L.CONSUMED_FWD_DIV / len(names)] * len(names)
+            bwd += [s["consumed_bwd"] / L.CONSUMED_BWD_DIV / len(names)] * len(names)
+        return {"fwd": fwd, "bwd": bwd}
+
+    def overflowed(self) -> bool:
+        return any(ps.status()["overflow"] for ps in self.passes.values())

@@ -68,6 +68,7 @@ _STATES_LOCK = threading.Lock()
 CAPACITY_MODE = os.environ.get("B2R_CAPACITY_MODE", "speculative")  # or "exact"
 CAPACITY_HEADROOM = 1.25
 TILE_CULL = os.environ.get("B2R_TILE_CULL", "1") != "0"
+SEGMENTED = os.environ.get("B2R_SEGMENTED", "1") != "0"  # checkpointed forward + segment-parallel backward
 # Fixed-capacity mode: every render uses this many list entries, nothing is polled or synchronised, so the call is
 # capturable in a CUDA graph (torch.cuda.graph) together with the caller's loss, backward and copies.  Overflow is
 # not repaired on the fly in this mode: check `overflowed()` after the step (outputs are truncated, never corrupt).
@@ -113,7 +114,7 @@ def _wait_mirror(st: _DeviceState, token: int, stream: torch.cuda.Stream, timeou
 
 class _Context:
     """What must survive from forward to backward (SURVEY.md section 8b 'Ownership')."""
-    __slots__ = ("scene", "ws", "keep", "ctx_buf", "dup_ids", "num_dups", "P", "W", "H", "M", "flags")
+    __slots__ = ("scene", "ws", "keep", "ctx_buf", "dup_ids", "num_dups", "P", "W", "H", "M", "flags", "ckpt")
 
 
 def _make_scene(settings: GaussianRasterizationSettings, means3D, shs, colors, opac, scales, rots, cov, flags, skin=None):
@@ -158,7 +159,9 @@ def _make_scene(settings: GaussianRasterizationSettings, means3D, shs, colors, o
     return sc, keep
 
 
-def _forward_impl(settings, means3D, shs, colors, opac, scales, rots, cov, want_stats=False, skin=None):
+def _forward_impl(settings, means3D, shs, colors, opac, scales, rots, cov, want_stats=False, skin=None, need_grad=True):
+    """need_grad: a backward may follow, so the forward composite also stores its blend-state checkpoints (the segmented
+    backward replays 256-entry list segments independently from them); inference calls skip that buffer."""
     lib = L.load()
     dev = means3D.device
     P = int(means3D.shape[0])
@@ -181,13 +184,20 @@ def _forward_impl(settings, means3D, shs, colors, opac, scales, rots, cov, want_
         ctx_buf = torch.empty(ctx_bytes, dtype=torch.uint8, device=dev)
         out = L.B2RForwardOutputs(color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), radii.data_ptr())
 
+        def checkpoints(cap):
+            if not (need_grad and SEGMENTED):
+                return None, 0
+            nbytes = lib.b2r_checkpoint_bytes(W, H, cap)
+            return torch.empty(nbytes, dtype=torch.uint8, device=dev), nbytes
+
         def workspace(cap, token):
             ids = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
             sbytes = lib.b2r_scratch_bytes(P, W, H, cap)
             scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
+            ck, ckb = checkpoints(cap)
             ws = L.B2RWorkspace(ctx_buf.data_ptr(), ctx_bytes, ids.data_ptr(), cap, scratch.data_ptr(), sbytes,
-                                st.mirror.data_ptr(), token)
-            return ws, ids, scratch
+                                st.mirror.data_ptr(), token, _ptr(ck), ckb)
+            return ws, ids, scratch, ck
 
         key = (P, W, H)
         if FIXED_CAPACITY is not None:
@@ -195,7 +205,9 @@ def _forward_impl(settings, means3D, shs, colors, opac, scales, rots, cov, want_
             ids = torch.empty(max(cap, 1), dtype=torch.int32, device=dev)
             sbytes = lib.b2r_scratch_bytes(P, W, H, cap)
             scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
-            ws = L.B2RWorkspace(ctx_buf.data_ptr(), ctx_bytes, ids.data_ptr(), cap, scratch.data_ptr(), sbytes, None, 0)
+            ck, ckb = checkpoints(cap)
+            ws = L.B2RWorkspace(ctx_buf.data_ptr(), ctx_bytes, ids.data_ptr(), cap, scratch.data_ptr(), sbytes, None, 0,
+                                _ptr(ck), ckb)
             L.check(lib.b2r_forward(C.byref(sc), C.byref(ws), C.byref(out), sptr), "b2r_forward")
             num = -1
         else:
@@ -204,17 +216,17 @@ def _forward_impl(settings, means3D, shs, colors, opac, scales, rots, cov, want_
               predicted = st.predicted.get(key) if CAPACITY_MODE == "speculative" else None
               if predicted is not None:
                   cap = int(predicted * CAPACITY_HEADROOM) + 4096
-                  ws, ids, scratch = workspace(cap, token)
+                  ws, ids, scratch, ck = workspace(cap, token)
                   L.check(lib.b2r_forward(C.byref(sc), C.byref(ws), C.byref(out), sptr), "b2r_forward")
                   num = _wait_mirror(st, token, stream)
                   if num > cap:  # misprediction: redo binning + composite with the exact size
-                      ws, ids, scratch = workspace(num, token)
+                      ws, ids, scratch, ck = workspace(num, token)
                       L.check(lib.b2r_forward_render(C.byref(sc), C.byref(ws), C.byref(out), sptr), "b2r_forward_render")
               else:
-                  ws0 = L.B2RWorkspace(ctx_buf.data_ptr(), ctx_bytes, None, 0, None, 0, st.mirror.data_ptr(), token)
+                  ws0 = L.B2RWorkspace(ctx_buf.data_ptr(), ctx_bytes, None, 0, None, 0, st.mirror.data_ptr(), token, None, 0)
                   L.check(lib.b2r_forward_project(C.byref(sc), C.byref(ws0), radii.data_ptr(), sptr), "b2r_forward_project")
                   num = _wait_mirror(st, token, stream)
-                  ws, ids, scratch = workspace(num, token)
+                  ws, ids, scratch, ck = workspace(num, token)
                   L.check(lib.b2r_forward_render(C.byref(sc), C.byref(ws), C.byref(out), sptr), "b2r_forward_render")
               st.predicted[key] = num
         # `scratch` may be recycled by the caching allocator as soon as we drop it: same-stream ordering makes that safe
@@ -225,7 +237,9 @@ def _forward_impl(settings, means3D, shs, colors, opac, scales, rots, cov, want_
         cx.scene, cx.ws, cx.keep, cx.ctx_buf, cx.dup_ids, cx.num_dups = sc, ws, keep, ctx_buf, ids, num
         cx.P, cx.W, cx.H, cx.M, cx.flags = P, W, H, sc.sh_coeffs, flags
         # the saved workspace must not point at the recycled scratch
-        cx.ws = L.B2RWorkspace(ctx_buf.data_ptr(), ctx_bytes, ids.data_ptr(), ws.dup_capacity, None, 0, None, 0)
+        cx.ckpt = ck
+        cx.ws = L.B2RWorkspace(ctx_buf.data_ptr(), ctx_bytes, ids.data_ptr(), ws.dup_capacity, None, 0, None, 0,
+                               ws.checkpoints, ws.checkpoint_bytes)
         if FIXED_CAPACITY is not None:
             RECENT_CONTEXTS.append(cx)
             del RECENT_CONTEXTS[:-64]
@@ -255,7 +269,7 @@ def read_status(cx: _Context) -> dict:
             "num_visible": int(s.num_visible), "consumed_fwd": int(s.consumed_fwd), "consumed_bwd": int(s.consumed_bwd)}
 
 
-def _backward_impl(cx: _Context, g_color, g_depth, g_alpha):
+def _backward_impl(cx: _Context, g_color, g_depth, g_alpha, g_posed=None):
     lib = L.load()
     keep = cx.keep
     dev = keep["means3D"].device
@@ -275,7 +289,8 @@ def _backward_impl(cx: _Context, g_color, g_depth, g_alpha):
         scratch = torch.empty(sbytes, dtype=torch.uint8, device=dev)
         args = L.B2RBackwardArgs(_ptr(g_color), _ptr(g_depth), _ptr(g_alpha), _ptr(d_means3D), _ptr(d_means2D),
                                  _ptr(d_shs), _ptr(d_colors), _ptr(d_opac), _ptr(d_scales), _ptr(d_rots), _ptr(d_cov),
-                                 0, 0, None, None, None, _ptr(d_xyz), _ptr(d_G))
+                                 0, 0, None, None, None, _ptr(d_xyz), _ptr(d_G),
+                                 None if g_posed is None else _ptr(_f32c(g_posed, "grad_posed")))
         L.check(lib.b2r_backward(C.byref(cx.scene), C.byref(cx.ws), C.byref(args), scratch.data_ptr(), sbytes,
                                  stream.cuda_stream), "b2r_backward")
         if cx.flags & L.B2R_FLAG_DEBUG:
@@ -293,7 +308,7 @@ class _RasterizeGaussians(torch.autograd.Function):
         args = (m3, opt(sh, "shs"), opt(colors_precomp, "colors_precomp"), _f32c(opacities, "opacities"),
                 opt(scales, "scales"), opt(rotations, "rotations"), opt(cov3Ds_precomp, "cov3D_precomp"))
         try:
-            color, radii, depth, alpha, cx = _forward_impl(raster_settings, *args)
+            color, radii, depth, alpha, cx = _forward_impl(raster_settings, *args, need_grad=any(ctx.needs_input_grad))
         except Exception:
             if raster_settings.debug:  # reference behaviour with debug=True: dump the arguments, re-raise
                 torch.save(tuple(None if a is None else a.cpu() for a in args), "snapshot_fw.dump")
@@ -389,23 +404,26 @@ class _RasterizeSkinned(torch.autograd.Function):
         posed = torch.empty((P, 3), dtype=torch.float32, device=dev)
         color, radii, depth, alpha, cx = _forward_impl(raster_settings, posed, None, _f32c(colors_precomp, "colors_precomp"),
                                                        _f32c(opacities, "opacities"), _f32c(scales, "scales"),
-                                                       _f32c(rotations, "rotations"), None, skin=skin)
+                                                       _f32c(rotations, "rotations"), None, skin=skin,
+                                                       need_grad=any(ctx.needs_input_grad))
         ctx.set_materialize_grads(False)
         ctx.cx = cx
         ctx.shapes = (means2D.shape, opacities.shape, joint_mats.shape, trans.shape)
-        ctx.mark_non_differentiable(radii, posed)
+        ctx.mark_non_differentiable(radii)
         return color, radii, depth, alpha, posed
 
     @staticmethod
     def backward(ctx, grad_color, grad_radii, grad_depth, grad_alpha, grad_posed):
         cx = ctx.cx
-        if grad_color is None and grad_depth is None and grad_alpha is None:
+        if grad_color is None and grad_depth is None and grad_alpha is None and grad_posed is None:
             return (None,) * 12
-        if grad_color is None:
-            ref = grad_depth if grad_depth is not None else grad_alpha
-            grad_color = torch.zeros((3,) + tuple(ref.shape[-2:]), dtype=torch.float32, device=ref.device)
+        if grad_color is None:  # only depth / alpha / the posed positions were used downstream
+            grad_color = torch.zeros((3, cx.H, cx.W), dtype=torch.float32, device=cx.keep["means3D"].device)
         m2s, ops, js, ts = ctx.shapes
-        _, d_m2, _, d_col, d_op, d_sc, d_rot, _, d_xyz, d_G = _backward_impl(cx, grad_color, grad_depth, grad_alpha)
+        # `posed` is differentiable: ExAvatar reads the posed mean_3d elsewhere (face_mesh_renderer, model.py:172-173, and
+        # the cat(scene.detach(), human) renders, model.py:117-125); its gradient joins dL/dworld inside the backward
+        # projection kernel, i.e. d_xyz += M^T Rinv^T g, d_G += (Rinv^T g) [x, 1]^T
+        _, d_m2, _, d_col, d_op, d_sc, d_rot, _, d_xyz, d_G = _backward_impl(cx, grad_color, grad_depth, grad_alpha, grad_posed)
         W = cx.keep["skin"]["weights"]
         J = W.shape[1]
         d_joint = torch.zeros((J, 4, 4), dtype=torch.float32, device=W.device)
@@ -425,8 +443,8 @@ class SkinnedGaussianRasterizer(nn.Module):
 
     xyz (P,3) canonical positions; skin_weights (P,J) rows gathered per Gaussian (module.py:414); joint_mats (J,4,4);
     trans (3); cam_R (3,3) / cam_t (3) or None to stay in the posed frame (`is_world_coord=True`).  `posed` (P,3) is the
-    world position ExAvatar's other modules read (non-differentiable output; the gradient flows through the fused
-    path to xyz, joint_mats and trans)."""
+    world position ExAvatar's other modules read; it is a differentiable output: a gradient arriving at it is added to
+    dL/dworld inside the backward projection kernel and reaches xyz, joint_mats and trans like the render's own."""
 
     def __init__(self, raster_settings):
         super().__init__()

@@ -33,7 +33,7 @@
 extern "C" {
 #endif
 
-#define B2R_ABI_VERSION 2
+#define B2R_ABI_VERSION 3
 
 #define B2R_OK 0
 #define B2R_E_INVALID (-1)      /* bad argument (null pointer, negative size, both / neither colour source ...) */
@@ -90,8 +90,8 @@ typedef struct B2RStatus {
   uint64_t dup_capacity;  /* capacity the render phase ran with */
   uint32_t overflow;      /* 1 if num_dups > dup_capacity: outputs are truncated, re-run with more room */
   uint32_t num_visible;   /* Gaussians with radii > 0 */
-  uint64_t consumed_fwd;  /* list entries staged by the forward composite (C_f of the roofline model) */
-  uint64_t consumed_bwd;  /* list entries staged by the backward composite (C_b) */
+  uint64_t consumed_fwd;  /* list entries staged by the forward composite per tile (C_f of the roofline model), x 8 */
+  uint64_t consumed_bwd;  /* list entries staged by the backward composite per tile (C_b), x 4 (one count per quarter tile) */
   uint64_t token;         /* B2RWorkspace.status_token of the project phase that filled this block */
   uint64_t reserved[2];
 } B2RStatus; /* 64 bytes */
@@ -108,7 +108,34 @@ typedef struct B2RWorkspace {
                               phase stores {num_dups, status_token} there (in that order) so the host can learn the
                               duplicate count by polling, without a stream synchronisation */
   uint64_t status_token;   /* caller-chosen, e.g. a call counter */
+  /* Optional (ABI v3): room for the segment table + per-pixel blend-state checkpoints the forward composite stores at
+   * every 256-entry cut of a tile's list, >= b2r_checkpoint_bytes(width, height, dup_capacity); saved until backward.
+   * With it the backward composite replays every (quarter tile, 256-entry segment) as an independent work item instead
+   * of walking a 2000-entry list on one warp.  NULL: lists are not cut (same results, longer serial chains). */
+  void* checkpoints;
+  size_t checkpoint_bytes;
 } B2RWorkspace;
+
+/* A VIEW of a binned scene (ABI v3).  ExAvatar renders one camera five times per training frame
+ * (avatar/main/model.py:130-162): the scene Gaussians, the human Gaussians, and cat(scene, human) -- the same
+ * projections, tile lists and depth order every time.  Project + bin cat(scene, human) ONCE (b2r_forward_project,
+ * b2r_forward_bin) and composite it several times, each view keeping only the Gaussians of an index range, with its own
+ * background and its own per-pixel state; b2r_backward_composite accumulates every view's screen-space gradients into
+ * one scratch, b2r_backward_project turns them into parameter gradients once. */
+typedef struct B2RView {
+  uint32_t id_begin, id_end; /* Gaussians [id_begin, id_end) take part; the others are skipped as if absent */
+  const float* bg;           /* (3) background of this view; NULL = scene->bg */
+  float* final_T;            /* (H*W) per-pixel final transmittance of this view, saved until its backward; NULL = in ctx */
+  uint32_t* n_contrib;       /* (H*W) per-pixel position of the last applied list entry; NULL = in ctx */
+  void* checkpoints;         /* this view's checkpoint store (see B2RWorkspace.checkpoints); NULL = the workspace's */
+  size_t checkpoint_bytes;
+  uint32_t skip_below;       /* != 0: tiles whose list holds no Gaussian of index >= skip_below are SKIPPED -- the forward
+                                leaves their pixels of `out` (and of final_T / n_contrib) untouched, the backward adds
+                                nothing for them.  For cat(scene.detach(), human) with skip_below = #scene: where no human
+                                Gaussian reaches a tile the combined render equals the scene-only view (copy its image
+                                into `out` first) and nothing of it carries gradient (model.py:117-125). */
+  uint32_t reserved;
+} B2RView;
 
 typedef struct B2RForwardOutputs {
   float* color;   /* (3,H,W) */
@@ -149,6 +176,14 @@ typedef struct B2RBackwardArgs {
    * Both follow `flags` (write / accumulate) and `first_row` like every other output. */
   float* dL_dskin_xyz;
   float* dL_dskin_G;
+  /* INPUT (ABI v3), (P,3) or NULL: gradient arriving at the posed world positions the forward wrote to
+   * B2RScene.skin_means_out (other ExAvatar modules read them: face_mesh_renderer, avatar/main/model.py:172-173); it is
+   * added to dL/dworld_i before the skinning transpose, so it reaches dL_dskin_xyz / dL_dskin_G (and dL_dmeans3D). */
+  const float* dL_dposed;
+  /* (ABI v3) the densification statistics above are updated for Gaussians [0, densify_rows) only; 0 = all.  A merged
+   * cat(scene, human) pass keeps ExAvatar's bookkeeping to the scene Gaussians this way (model.py:193). */
+  uint32_t densify_rows;
+  uint32_t reserved;
 } B2RBackwardArgs;
 #define B2R_BWD_ACCUMULATE 1u
 /* The caller guarantees `bwd_scratch` is all zero on entry; b2r_backward then skips its memset and leaves the scratch
@@ -160,12 +195,13 @@ int b2r_abi_version(void);
 const char* b2r_strerror(int code);
 int b2r_last_cuda_error(void);
 /* sizeof() of the ABI structs, for bindings to verify their mirror: 0 B2RScene, 1 B2RStatus, 2 B2RWorkspace,
- * 3 B2RForwardOutputs, 4 B2RBackwardArgs; 0 for anything else. */
+ * 3 B2RForwardOutputs, 4 B2RBackwardArgs, 5 B2RView; 0 for anything else. */
 size_t b2r_sizeof(int which);
 
 size_t b2r_ctx_bytes(int32_t P, int32_t width, int32_t height);
 size_t b2r_scratch_bytes(int32_t P, int32_t width, int32_t height, uint64_t dup_capacity);
 size_t b2r_backward_scratch_bytes(int32_t P);
+size_t b2r_checkpoint_bytes(int32_t width, int32_t height, uint64_t dup_capacity);
 
 /* Phase A: projection, tile counting, tile scan.  Writes radii and B2RStatus.num_dups. */
 int b2r_forward_project(const B2RScene* scene, const B2RWorkspace* ws, int32_t* radii, void* stream);
@@ -177,6 +213,21 @@ int b2r_forward(const B2RScene* scene, const B2RWorkspace* ws, const B2RForwardO
 /* Backward composite + backward projection.  `ws` is the forward's; `bwd_scratch` >= b2r_backward_scratch_bytes(P). */
 int b2r_backward(const B2RScene* scene, const B2RWorkspace* ws, const B2RBackwardArgs* args, void* bwd_scratch,
                  size_t bwd_scratch_bytes, void* stream);
+
+/* The same pipeline in separately callable stages (ABI v3), for several views of one binned scene:
+ *   b2r_forward_project -> b2r_forward_bin -> b2r_forward_composite (once per view)
+ *   b2r_backward_composite (once per view, same scratch) -> b2r_backward_project (once).
+ * b2r_forward_render == bin + composite(view = NULL); b2r_backward == composite(view = NULL) + project.
+ * b2r_backward_composite reads only dL_dcolor / dL_ddepth / dL_dalpha, `flags` (B2R_BWD_SCRATCH_ZEROED: the caller zeroed
+ * the scratch before the FIRST view; later views must pass it too, so nothing is cleared in between) and `first_row`
+ * (Gaussians below it receive nothing from this view: the detached prefix of cat(scene.detach(), human)). */
+int b2r_forward_bin(const B2RScene* scene, const B2RWorkspace* ws, void* stream);
+int b2r_forward_composite(const B2RScene* scene, const B2RWorkspace* ws, const B2RView* view,
+                          const B2RForwardOutputs* out, void* stream);
+int b2r_backward_composite(const B2RScene* scene, const B2RWorkspace* ws, const B2RView* view, const B2RBackwardArgs* args,
+                           void* bwd_scratch, size_t bwd_scratch_bytes, void* stream);
+int b2r_backward_project(const B2RScene* scene, const B2RWorkspace* ws, const B2RBackwardArgs* args, void* bwd_scratch,
+                         size_t bwd_scratch_bytes, void* stream);
 
 /* present[i] = 1 iff Gaussian i passes the near-plane test (z_view > 0.2). */
 int b2r_mark_visible(int32_t P, const float* means3D, const float* viewmatrix, uint8_t* present, void* stream);

@@ -31,8 +31,8 @@ def test_library_exports_every_declared_symbol():
 
 def test_struct_layouts_and_version():
     lib = L.load()
-    assert lib.b2r_abi_version() == 2
-    for idx, cls in enumerate((L.B2RScene, L.B2RStatus, L.B2RWorkspace, L.B2RForwardOutputs, L.B2RBackwardArgs)):
+    assert lib.b2r_abi_version() == 3 == L.ABI_VERSION
+    for idx, cls in enumerate((L.B2RScene, L.B2RStatus, L.B2RWorkspace, L.B2RForwardOutputs, L.B2RBackwardArgs, L.B2RView)):
         assert lib.b2r_sizeof(idx) == C.sizeof(cls)
     assert lib.b2r_sizeof(99) == 0
     assert C.sizeof(L.B2RStatus) == 64
@@ -48,6 +48,11 @@ def test_size_queries():
     assert lib.b2r_scratch_bytes(1000, 64, 64, 1 << 20) >= 8 << 20
     assert lib.b2r_backward_scratch_bytes(1000) >= 48000
     assert lib.b2r_ctx_bytes(0, 16, 16) > 0
+    # checkpoint store: a segment table + 6 KB per 256-entry cut; grows with the duplicate capacity and the tile count
+    c0 = lib.b2r_checkpoint_bytes(64, 64, 0)
+    c1 = lib.b2r_checkpoint_bytes(64, 64, 1 << 20)
+    assert 0 < c0 < c1 and c1 >= (1 << 20) // 256 * 6144
+    assert lib.b2r_checkpoint_bytes(512, 512, 0) > c0
 
 
 def test_error_codes_without_touching_cuda():
@@ -145,3 +150,55 @@ def test_error_codes_of_the_round1_additions_without_touching_cuda():
     assert bwd(fake, 8) == -2               # scratch too small
     args.first_row = 11
     assert bwd(fake, 1 << 20) == -1
+
+
+def test_error_codes_of_the_abi_v3_entry_points_without_touching_cuda():
+    """Views, the split pipeline stages, the checkpoint store and the posed-position gradient are validated on the host."""
+    lib = L.load()
+    fake = 0x1000
+    sc = L.B2RScene()
+    sc.P, sc.width, sc.height, sc.tanfovx, sc.tanfovy = 10, 32, 32, 0.5, 0.5
+    sc.bg = sc.viewmatrix = sc.projmatrix = sc.campos = fake
+    sc.means3D = sc.opacities = sc.colors_precomp = sc.scales = sc.rotations = fake
+    ws = L.B2RWorkspace()
+    ws.ctx, ws.ctx_bytes = fake, lib.b2r_ctx_bytes(10, 32, 32)
+    ws.dup_ids, ws.dup_capacity = fake, 1000
+    out = L.B2RForwardOutputs()
+    view = L.B2RView()
+    comp = lambda: lib.b2r_forward_composite(C.byref(sc), C.byref(ws), C.byref(view), C.byref(out), None)
+    assert comp() == -1                      # no output images
+    out.color = out.depth = out.alpha = fake
+    view.id_begin, view.id_end = 4, 2
+    assert comp() == -1                      # empty / inverted Gaussian range
+    view.id_begin, view.id_end = 0, 11
+    assert comp() == -1                      # range beyond P
+    view.id_begin, view.id_end = 2, 10
+    view.final_T = fake
+    assert comp() == -1                      # final_T and n_contrib come as a pair
+    view.final_T = None
+    # an undersized checkpoint store is rejected before anything is launched
+    ws.checkpoints, ws.checkpoint_bytes = fake, 16
+    assert comp() == -2
+    ws.checkpoint_bytes = lib.b2r_checkpoint_bytes(32, 32, 1000)
+    view.checkpoints, view.checkpoint_bytes = fake, 16
+    assert comp() == -2                      # ... and so is a view's own store
+    # binning needs the scratch
+    assert lib.b2r_forward_bin(C.byref(sc), C.byref(ws), None) == -1
+    ws.scratch, ws.scratch_bytes = fake, 8
+    assert lib.b2r_forward_bin(C.byref(sc), C.byref(ws), None) == -2
+    # backward stages
+    args = L.B2RBackwardArgs()
+    view = L.B2RView()
+    view.id_begin, view.id_end = 0, 10
+    bc = lambda scratch, n: lib.b2r_backward_composite(C.byref(sc), C.byref(ws), C.byref(view), C.byref(args), scratch, n, None)
+    bp = lambda scratch, n: lib.b2r_backward_project(C.byref(sc), C.byref(ws), C.byref(args), scratch, n, None)
+    assert bc(fake, 1 << 20) == -1           # no dL_dcolor
+    args.dL_dcolor = fake
+    assert bc(fake, 8) == -2 and bp(fake, 8) == -2
+    assert bp(None, 1 << 20) == -1
+    args.first_row = 11
+    assert bc(fake, 1 << 20) == -1 and bp(fake, 1 << 20) == -1
+    args.first_row = 0
+    args.dL_dposed = fake                    # a posed-position gradient only makes sense with fused skinning
+    assert bp(fake, 1 << 20) == -1
+    assert lib.b2r_backward(C.byref(sc), C.byref(ws), C.byref(args), fake, 1 << 20, None) == -1

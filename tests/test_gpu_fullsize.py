@@ -12,7 +12,7 @@ import pytest
 import torch
 
 from parity import compare, contributor_report, last_contributor
-from util import kat_settings, workload_settings
+from util import kat_settings, settings_on, workload_settings
 from exavatar_release_b200.synthetic import WORKLOADS, make_assets, make_grad_image, make_population_assets
 from oracle import oracle as O
 
@@ -54,11 +54,11 @@ def _plan_vs_oracle(dev, case, wl_name, yaw, seed=0, cap=12_000_000, with_da=Fal
     assets = make_assets(wl_name, seed=seed)
     bg = (0.2, 0.6, 0.9)
     st_c = workload_settings(wl_name, yaw=yaw, bg=bg)
-    st_g = workload_settings(wl_name, yaw=yaw, bg=bg, device=dev, settings_cls=rz.GaussianRasterizationSettings)
     use_sh = wl.sh_degree > 0
     M = (wl.sh_degree + 1) ** 2 if use_sh else 0
     if use_sh:
-        st_c, st_g = st_c._replace(sh_degree=wl.sh_degree), st_g._replace(sh_degree=wl.sh_degree)
+        st_c = st_c._replace(sh_degree=wl.sh_degree)
+    st_g = settings_on(st_c, dev, rz.GaussianRasterizationSettings)
     kw = dict(shs=assets["shs"]) if use_sh else dict(colors_precomp=assets["rgb"])
     oc, orad, od, oa, octx = O.forward(st_c, assets["mean_3d"], assets["opacity"], scales=assets["scale"],
                                        rotations=assets["rotation"], **kw)
@@ -119,14 +119,17 @@ def test_c4_single_render_parity(dev):
     _plan_vs_oracle(dev, "C4", "C4", yaw=15.0)
 
 
-def test_c4_five_render_frame_vs_five_oracle_renders(dev):
+@pytest.mark.parametrize("engine", ["merged", "separate"])
+def test_c4_five_render_frame_vs_five_oracle_renders(dev, engine):
     """BASELINE configs[3]: one training frame of avatar/main/model.py:81-162 at full size (167 k human + 130 k scene
     Gaussians, 512x512) on FiveRenderPlan, every render against ITS OWN oracle render: scene | human (random bg) |
     cat(scene.detach(), human) | human_refined | cat(scene.detach(), human_refined).  Gradients: the scene bucket is the
-    scene render's; the human bucket is render 2 + the human rows of render 3 (the detached prefix gets nothing)."""
+    scene render's; the human bucket is render 2 + the human rows of render 3 (the detached prefix gets nothing).
+    engine "merged": MergedFivePlan (two projection / binning passes, five views -- SURVEY 8f-3); "separate": five
+    independent renders (FiveRenderPlan)."""
     from exavatar_release_b200 import rasterizer as rz
     from exavatar_release_b200.camera import look_at_cam_param
-    from exavatar_release_b200.plan import RENDERS, FiveRenderPlan, _views_of
+    from exavatar_release_b200.plan import RENDERS, FiveRenderPlan, MergedFivePlan
     from exavatar_release_b200.renderer import render_settings
     wl = WORKLOADS["C4"]
     H, W = wl.height, wl.width
@@ -147,11 +150,10 @@ def test_c4_five_render_frame_vs_five_oracle_renders(dev):
         ora[r] = dict(color=oc, radii=orad, alpha=oa, grads=og, frag=O.fragility(octx), ctx=octx)
 
     to = lambda d: {k: v.to(dev) for k, v in d.items()}
-    camg = {k: v.to(dev) for k, v in cam.items()}
-    plan = FiveRenderPlan(Ps, Ph, W, H, {r: 6_000_000 for r in RENDERS}, dev)
+    plan = (MergedFivePlan if engine == "merged" else FiveRenderPlan)(Ps, Ph, W, H, None, dev)
     plan.set_scene(to(scene))
-    st_w = render_settings((H, W), camg, bg_w.to(dev))
-    st_r = render_settings((H, W), camg, bg_r.to(dev))
+    st_w = settings_on(render_settings((H, W), cam, bg_w, O.OracleSettings), dev, rz.GaussianRasterizationSettings)
+    st_r = settings_on(render_settings((H, W), cam, bg_r, O.OracleSettings), dev, rz.GaussianRasterizationSettings)
     plan.frame(0, st_w, st_r, to(scene), to(human), to(refined), {r: g.to(dev) for r, g in gcol.items()}, accumulate=False)
     torch.cuda.synchronize()
     assert not plan.overflowed()
@@ -160,12 +162,12 @@ def test_c4_five_render_frame_vs_five_oracle_renders(dev):
         pm, _ = ora[r]["frag"]
         img, alpha, radii = plan.render_outputs(r)
         assert np.array_equal(radii.cpu().numpy(), ora[r]["radii"]), r
-        compare("C4/" + r, "color", img.cpu().numpy(), ora[r]["color"], pm[None], kind="image")
-        compare("C4/" + r, "alpha", alpha.cpu().numpy(), ora[r]["alpha"], pm[None], kind="image")
+        compare(f"C4-{engine}/" + r, "color", img.cpu().numpy(), ora[r]["color"], pm[None], kind="image")
+        compare(f"C4-{engine}/" + r, "alpha", alpha.cpu().numpy(), ora[r]["alpha"], pm[None], kind="image")
     # gradients: three parameter sets
     names = {"means3D": "means3D", "means2D": "means2D", "opacities": "opacities", "scales": "scales",
              "rotations": "rotations", "colors": "colors"}
-    b_scene, b_human, b_refined = plan.reduce()
+    plan.reduce()
 
     def expect(parts):
         out, flag = {}, None
@@ -177,14 +179,14 @@ def test_c4_five_render_frame_vs_five_oracle_renders(dev):
             flag = gm[rows] if flag is None else (flag | gm[rows])
         return out, flag
 
-    for label, bucket, Pn, parts in (
-            ("scene", b_scene, Ps, [("scene", slice(0, Ps))]),
-            ("human", b_human, Ph, [("human", slice(0, Ph)), ("scene_human", slice(Ps, Ps + Ph))]),
-            ("refined", b_refined, Ph, [("human_refined", slice(0, Ph)), ("scene_human_refined", slice(Ps, Ps + Ph))])):
-        _, views = _views_of(bucket, Pn)
+    for label, Pn, parts in (
+            ("scene", Ps, [("scene", slice(0, Ps))]),
+            ("human", Ph, [("human", slice(0, Ph)), ("scene_human", slice(Ps, Ps + Ph))]),
+            ("human_refined", Ph, [("human_refined", slice(0, Ph)), ("scene_human_refined", slice(Ps, Ps + Ph))])):
+        views = plan.grads(label)
         y, flag = expect(parts)
         for k in names:
-            compare("C4/" + label, "d_" + k, views[k].cpu().numpy().reshape(Pn, -1), y[k], flag[:, None], kind="grad")
+            compare(f"C4-{engine}/" + label, "d_" + k, views[k].cpu().numpy().reshape(Pn, -1), y[k], flag[:, None], kind="grad")
 
 
 def _stack_in_one_tile(n, seed):
@@ -213,7 +215,7 @@ def test_long_list_sort_is_bit_exact(dev, n):
     a = _stack_in_one_tile(n, seed=n)
     W, H = 64, 48
     st_c = kat_settings(W=W, H=H, f=60.0, bg=(0.1, 0.2, 0.3))
-    st_g = kat_settings(W=W, H=H, f=60.0, bg=(0.1, 0.2, 0.3), device=dev, settings_cls=rz.GaussianRasterizationSettings)
+    st_g = settings_on(st_c, dev, rz.GaussianRasterizationSettings)
     oc, orad, od, oa, octx = O.forward(st_c, a["mean_3d"], a["opacity"], colors_precomp=a["rgb"], scales=a["scale"],
                                        rotations=a["rotation"])
     o_ids, o_ranges = octx.sorted_ids(), octx.ranges()

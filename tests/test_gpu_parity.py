@@ -495,13 +495,15 @@ def test_unused_outputs_get_no_materialised_gradients(dev):
     assert float(lv1["rgb"].grad.abs().max()) == 0.0
 
 
-def test_five_render_plan_matches_the_reference_pattern(dev):
-    """FiveRenderPlan (five concurrent renders, detached scene prefix via `first_row`) == ExAvatar's pattern written
+@pytest.mark.parametrize("engine", ["merged", "separate"])
+def test_five_render_plan_matches_the_reference_pattern(dev, engine):
+    """FiveRenderPlan (five concurrent renders, detached scene prefix via `first_row`) and MergedFivePlan (two merged
+    projection / binning passes, five views) == ExAvatar's pattern written
     with the public autograd API: renderer(scene), renderer(human, bg), renderer(cat(scene.detach(), human)), and the
     same two for the refined human (avatar/main/model.py:81-162), two frames accumulated."""
     from exavatar_release_b200 import GaussianRenderer
     from exavatar_release_b200.camera import look_at_cam_param
-    from exavatar_release_b200.plan import RENDERS, FiveRenderPlan
+    from exavatar_release_b200.plan import RENDERS, FiveRenderPlan, MergedFivePlan
     from exavatar_release_b200.renderer import render_settings
     from exavatar_release_b200.synthetic import make_population_assets
     rz = RZ()
@@ -527,7 +529,7 @@ def test_five_render_plan_matches_the_reference_pattern(dev):
         loss = loss + sum((imgs[r] * gcol[f][r]).sum() for r in RENDERS)
     loss.backward()
 
-    plan = FiveRenderPlan(Ps, Ph, W, H, {r: 2_000_000 for r in RENDERS}, dev)
+    plan = (MergedFivePlan if engine == "merged" else FiveRenderPlan)(Ps, Ph, W, H, None, dev)
     plan.set_scene(scene)
     for f, cam in enumerate(cams):
         st_w = render_settings((H, W), cam, bg_w)
@@ -536,9 +538,9 @@ def test_five_render_plan_matches_the_reference_pattern(dev):
     torch.cuda.synchronize()
     assert not plan.overflowed()
     names = {"mean_3d": "means3D", "opacity": "opacities", "scale": "scales", "rotation": "rotations", "rgb": "colors"}
-    from exavatar_release_b200.plan import _views_of
-    for bucket, leaves, P in zip(plan.reduce(), (lv["scene"], lv["human"], lv["refined"]), (Ps, Ph, Ph)):
-        _, views = _views_of(bucket, P)
+    plan.reduce()
+    for which, leaves, P in zip(("scene", "human", "human_refined"), (lv["scene"], lv["human"], lv["refined"]), (Ps, Ph, Ph)):
+        views = plan.grads(which)
         for k, n in names.items():
             ref = leaves[k].grad.reshape(P, -1)
             assert torch.allclose(views[n], ref, rtol=1e-4, atol=1e-5 * float(ref.abs().max()) + 1e-12), (k, P)

@@ -52,3 +52,15 @@ def rel_err(x, y, floor):
     if x.size == 0:
         return 0.0
     return float(np.max(np.abs(x - y) / np.maximum(np.abs(y), floor)))
+
+
+def settings_on(st, device, settings_cls):
+    """The SAME settings (bit for bit) with their tensors on `device`, as another settings class.  Camera matrices built
+    on different devices can differ in the last bit (atan / tan / inverse / mm), which flips radius and tile-rect
+    decisions for a few of 10^5 Gaussians; parity tests therefore build them once (CPU) and hand both paths the same bits."""
+    import torch
+    d = st._asdict()
+    for k, v in d.items():
+        if isinstance(v, torch.Tensor):
+            d[k] = v.to(device)
+    return settings_cls(**d)
