@@ -16,6 +16,7 @@ ABI_VERSION = 3
 B2R_OK = 0
 B2R_FLAG_NO_TILE_CULL = 1
 B2R_FLAG_DEBUG = 2
+B2R_FLAG_CTX_CLEAN = 4
 
 _fp = C.c_void_p  # device pointers travel as plain addresses
 

@@ -41,7 +41,8 @@ enum { CLS_N_LARGE = 0,   // tiles with >= 2048 entries (sorted in chunks)
        CLS_N_MULTI = 2,   // tiles cut into segments (>= 256 entries), 0 when the caller gave no checkpoint buffer
        CLS_N_CHUNKS = 3,  // sort chunks of the large tiles
        CLS_TOTAL_SEGS = 4,  // segments of the multi-segment tiles
-       CLS_N_GE1024 = 5,    // tiles with >= 1024 entries (alternative heavy threshold of the forward composite)
+       CLS_N_GE1024 = 5,    // tiles with >= 1024 entries
+       CLS_VIS_ACC = 6,     // visible-Gaussian accumulator of the projection kernel (published to B2RStatus by the scan)
        CLS_COUNT = 8 };
 constexpr size_t ALIGN = 256;
 __host__ __device__ inline size_t align_up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }

@@ -46,33 +46,29 @@ __device__ __forceinline__ float rcp_approx4(float x) {
   return y;
 }
 
-template <bool HAS_DA>
-__global__ void __launch_bounds__(B4_THREADS, B4_MIN_BLOCKS) composite_bwd4_kernel(const B2RScene sc, const Ctx cx,
-                                                                    const B2RBackwardArgs args, float* __restrict__ gacc) {
-  __shared__ B4Stage stage[2];
-  __shared__ B4Compact compact[2];
-  __shared__ float2 tb[2][B4_QUEUE][33];  // [warp][queued splat][pixel], padded rows: conflict-free both ways
-  __shared__ float4 qm0[2][B4_QUEUE];     // px, py, A2, B2
-  __shared__ float4 qm1[2][B4_QUEUE];     // C2, opacity, id bits, -
-  __shared__ float4 gpix[2][32];          // per pixel of the warp: g_r, g_g, g_b, g_depth
-  __shared__ int warp_max_s[2];
-  B2R_TRACE_BEGIN();
+struct B4Smem {
+  B4Stage stage[2];
+  B4Compact compact[2];
+  float2 tb[2][B4_QUEUE][33];  // [warp][queued splat][pixel], padded rows: conflict-free both ways
+  float4 qm0[2][B4_QUEUE];     // px, py, A2, B2
+  float4 qm1[2][B4_QUEUE];     // C2, opacity, id bits, -
+  float4 gpix[2][32];          // per pixel of the warp: g_r, g_g, g_b, g_depth
+  int warp_max_s[2];
+};
 
-  // ---- which (tile, segment, quarter) ----
-  const int s_item = blockIdx.x >> 2;
-  const int quad = blockIdx.x & 3;
-  const int n_multi = cx.ckpt ? (int)cx.classes[CLS_N_MULTI] : 0;
-  const int total_segs = cx.ckpt ? (int)cx.classes[CLS_TOTAL_SEGS] : 0;
-  int t_pos, seg;
-  if (s_item < total_segs) {
-    const uint2 e = cx.seg_table[s_item];
-    t_pos = (int)e.x;
-    seg = (int)e.y;
-  } else {
-    t_pos = n_multi + (s_item - total_segs);
-    seg = 0;
-    if (t_pos >= cx.tiles) return;
-  }
+// one work item: quarter `quad` of segment `seg` of the tile at position `t_pos` of cx.tile_order
+template <bool HAS_DA>
+__device__ __forceinline__ void bwd4_item(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& args,
+                                          float* __restrict__ gacc, B4Smem& sm, const int t_pos, const int seg,
+                                          const int quad, const int n_multi) {
+  B4Stage (&stage)[2] = sm.stage;
+  B4Compact (&compact)[2] = sm.compact;
+  float2 (&tb)[2][B4_QUEUE][33] = sm.tb;
+  float4 (&qm0)[2][B4_QUEUE] = sm.qm0;
+  float4 (&qm1)[2][B4_QUEUE] = sm.qm1;
+  float4 (&gpix)[2][32] = sm.gpix;
+  int (&warp_max_s)[2] = sm.warp_max_s;
+  B2R_TRACE_BEGIN();
   const bool multi = t_pos < n_multi;
   const int tile = (int)cx.tile_order[t_pos];
   // a view whose own Gaussians (index >= skip_below) do not occur in this tile has nothing to accumulate here: in
@@ -336,12 +332,41 @@ __global__ void __launch_bounds__(B4_THREADS, B4_MIN_BLOCKS) composite_bwd4_kern
   B2R_TRACE_END(nmax);
 }
 
+// The number of work items -- 4 quarter tiles x (segments of the multi-segment tiles + one per remaining tile) -- is only
+// known on the device, so the grid is a fixed number of CTAs that stride over the items (heaviest first: the item order
+// follows cx.tile_order).  A grid sized for the host-side worst case (capacity / 256 segments) would be mostly CTAs that
+// read two counters and exit -- 185 000 of 191 000 with a generously sized workspace (profiles/r02_notes.md).
+template <bool HAS_DA>
+__global__ void __launch_bounds__(B4_THREADS, B4_MIN_BLOCKS) composite_bwd4_kernel(const B2RScene sc, const Ctx cx,
+                                                                    const B2RBackwardArgs args, float* __restrict__ gacc) {
+  __shared__ B4Smem sm;
+  const int n_multi = cx.ckpt ? (int)cx.classes[CLS_N_MULTI] : 0;
+  const int total_segs = cx.ckpt ? (int)cx.classes[CLS_TOTAL_SEGS] : 0;
+  const int items = 4 * (total_segs + (cx.tiles - n_multi));
+  for (int item = blockIdx.x; item < items; item += gridDim.x) {
+    const int s_item = item >> 2;
+    int t_pos, seg;
+    if (s_item < total_segs) {
+      const uint2 e = cx.seg_table[s_item];
+      t_pos = (int)e.x;
+      seg = (int)e.y;
+    } else {
+      t_pos = n_multi + (s_item - total_segs);
+      seg = 0;
+    }
+    bwd4_item<HAS_DA>(sc, cx, args, gacc, sm, t_pos, seg, item & 3, n_multi);
+    __syncthreads();  // shared memory is reused by the next item
+  }
+}
+
 int launch_composite_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, float* gacc, cudaStream_t st) {
   if (!(a.flags & B2R_BWD_SCRATCH_ZEROED)) cudaMemsetAsync(gacc, 0, (size_t)(sc.P > 0 ? sc.P : 1) * 12 * sizeof(float), st);
-  // items: 4 quarter tiles x (segments of the multi-segment tiles + one per remaining tile).  The split is only known on
-  // the device; host-side bound: every segment beyond a tile's first covers 256 list entries.
+  // host-side bound on the item count (every segment beyond a tile's first covers 256 list entries), capped at a few
+  // waves of resident CTAs: the kernel strides over the items
   const uint64_t extra = cx.ckpt ? cx.dup_capacity / SEG : 0;
-  const unsigned grid = (unsigned)(4ull * ((uint64_t)cx.tiles + extra));
+  const uint64_t bound = 4ull * ((uint64_t)cx.tiles + extra);
+  const uint64_t cap = (uint64_t)device_sm_count() * B4_MIN_BLOCKS * 4;
+  const unsigned grid = (unsigned)(bound < cap ? bound : cap);
   ProfScope p(K_COMPOSITE_BWD, st);
   if (a.dL_ddepth || a.dL_dalpha)
     launch_k(composite_bwd4_kernel<true>, grid, B4_THREADS, 0, st, false, sc, cx, a, gacc);

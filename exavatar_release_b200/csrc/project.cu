@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
                             [&](int tx, int ty, uint32_t, uint32_t) { atomicAdd(tile_count + ty * gx + tx, 1u); });
   }
   const unsigned vis = __ballot_sync(0xffffffffu, visible);
-  if ((threadIdx.x & 31) == 0 && vis) atomicAdd(&cx.status->num_visible, (uint32_t)__popc(vis));
+  if ((threadIdx.x & 31) == 0 && vis) atomicAdd(&cx.classes[CLS_VIS_ACC], (uint32_t)__popc(vis));
   if (aggregate) {
     __syncthreads();
     for (int t = threadIdx.x; t < cx.tiles; t += blockDim.x) {
@@ -196,7 +196,10 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
 
 // Exclusive scan of the per-tile counts (one block; tiles <= a few 10^4).  Writes ranges[t] = [start, end) clamped to
 // the duplicate capacity, primes the scatter cursors with `start`, and publishes the total.
-__global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx) {
+// `final`: this scan's ranges are the ones the binning will use (a duplicate capacity was given), so the per-tile
+// counters are consumed: the kernel leaves them -- and the other accumulators of the ctx -- zero for the next render,
+// which can then skip status_reset_kernel (B2R_FLAG_CTX_CLEAN).
+__global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx, const int final) {
   __shared__ uint64_t warp_sums[32];
   __shared__ uint64_t carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -326,8 +329,18 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx) {
     const uint32_t c = (r.y - r.x + SEG - 1) / SEG, s0 = cx.seg_start[t];
     for (uint32_t k = 0; k < c; k++) cx.seg_table[s0 + k] = make_uint2(t, k);
   }
+  if (final) {  // every read of the counters happened before the barrier above
+    for (int t = threadIdx.x; t < cx.tiles; t += blockDim.x) {
+      cx.tile_count[t] = 0u;
+      cx.tile_maxid[t] = 0u;
+    }
+  }
   if (threadIdx.x == 0) {
     const uint64_t total = carry_s;
+    cx.status->num_visible = cx.classes[CLS_VIS_ACC];
+    if (final) cx.classes[CLS_VIS_ACC] = 0u;
+    cx.status->consumed_fwd = 0;
+    cx.status->consumed_bwd = 0;
     cx.status->num_dups = total;
     cx.status->dup_capacity = cx.dup_capacity;
     cx.status->overflow = total > cx.dup_capacity ? 1u : 0u;
@@ -355,6 +368,7 @@ __global__ void status_reset_kernel(const Ctx cx) {
     s->num_visible = 0;
     s->consumed_fwd = 0;
     s->consumed_bwd = 0;
+    cx.classes[CLS_VIS_ACC] = 0u;
   }
 }
 
@@ -368,7 +382,8 @@ __global__ void mark_visible_kernel(int P, const float* __restrict__ means3D, co
 }
 
 int launch_project(const B2RScene& sc, const Ctx& cx, int32_t* radii, cudaStream_t st) {
-  { ProfScope p(K_MISC, st); launch_k(status_reset_kernel, (cx.tiles + 1023) / 1024, 1024, 0, st, true, cx); }
+  const bool clean = (sc.flags & B2R_FLAG_CTX_CLEAN) != 0;  // the previous render's final scan left the counters zero
+  if (!clean) { ProfScope p(K_MISC, st); launch_k(status_reset_kernel, (cx.tiles + 1023) / 1024, 1024, 0, st, true, cx); }
   if (sc.P > 0) {
     ProfScope p(K_PROJECT, st);
     const int aggregate = cx.tiles <= 2048;  // beyond that the per-CTA sweeps over the tile table cost more than they save
@@ -378,13 +393,13 @@ int launch_project(const B2RScene& sc, const Ctx& cx, int32_t* radii, cudaStream
     cudaFuncSetAttribute(project_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024);  // per device
     launch_k(project_kernel, (sc.P + 255) / 256, 256, smem, st, true, sc, cx, radii, aggregate);
   }
-  { ProfScope p(K_TILE_SCAN, st); launch_k(tile_scan_kernel, 1, 1024, 0, st, true, cx); }
+  { ProfScope p(K_TILE_SCAN, st); launch_k(tile_scan_kernel, 1, 1024, 0, st, true, cx, cx.dup_capacity > 0 ? 1 : 0); }
   return check_launch();
 }
 
 void launch_tile_scan(const Ctx& cx, cudaStream_t st) {
   ProfScope p(K_TILE_SCAN, st);
-  launch_k(tile_scan_kernel, 1, 1024, 0, st, true, cx);
+  launch_k(tile_scan_kernel, 1, 1024, 0, st, true, cx, 1);
 }
 
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t st) {

@@ -52,6 +52,7 @@ class FramePlan:
         self.out = L.B2RForwardOutputs(self.color.data_ptr(), self.depth.data_ptr(), self.alpha.data_ptr(),
                                        self.radii.data_ptr())
         self._scenes = {}
+        self._primed = False
 
     def scene(self, key, settings, assets: Dict[str, torch.Tensor], flags: int = 0):
         """Builds (and caches under `key`) the B2RScene for one frame; tensors must stay alive and in place."""
@@ -65,9 +66,14 @@ class FramePlan:
         return sc
 
     def forward(self, sc) -> None:
+        # from the second forward on the ctx counters are known to be zero (every forward leaves them so): no reset launch
+        base = sc.flags & ~L.B2R_FLAG_CTX_CLEAN
+        sc.flags = base | (L.B2R_FLAG_CTX_CLEAN if self._primed else 0)
         with torch.cuda.device(self.device):
             st = torch.cuda.current_stream(self.device).cuda_stream
             L.check(self.lib.b2r_forward(C.byref(sc), C.byref(self.ws), C.byref(self.out), st), "b2r_forward")
+        sc.flags = base
+        self._primed = True
 
     def backward(self, sc, g_color: torch.Tensor, grads: Dict[str, Optional[torch.Tensor]], accumulate: bool = False,
                  g_depth: Optional[torch.Tensor] = None, g_alpha: Optional[torch.Tensor] = None,
@@ -314,6 +320,7 @@ class _Pass:
         widths = {"mean_3d": 3, "opacity": 1, "scale": 3, "rotation": 4, "rgb": 3}
         self.cat = {k: f(P, w) for k, w in widths.items()}
         self.streams = [torch.cuda.Stream(dev) for _ in range(n_views)]
+        self.primed = False
 
     def status(self) -> dict:
         raw = self.ctx_buf[: C.sizeof(L.B2RStatus)].cpu().numpy().tobytes()
@@ -380,8 +387,9 @@ class MergedFivePlan:
     def _view(self, ps, v, name, bg):
         lo, hi = self.ranges[name]
         fT, nc = ps.state[v]
-        # combined views: tiles no human Gaussian reaches equal the scene-only view and carry no gradient -> skipped
-        skip = self.Ps if (self.SKIP and name in ("scene_human", "scene_human_refined")) else 0
+        # Tiles no human Gaussian reaches: a combined view equals the scene-only view there and carries no gradient; a
+        # human-only view shows the bare background there.  Both are pre-filled by the caller and skipped by the kernels.
+        skip = self.Ps if (self.SKIP and name != "scene") else 0
         return L.B2RView(lo, hi, _ptr(bg), fT.data_ptr(), nc.data_ptr(), ps.ck[v].data_ptr(), ps.ck_bytes, skip, 0)
 
     def frame(self, key, settings, settings_human_bg, scene, human, refined, g_colors: Dict[str, torch.Tensor],
@@ -403,6 +411,8 @@ class MergedFivePlan:
                 for k, buf in ps.cat.items():
                     buf[self.Ps:].copy_(src[k].reshape(self.Ph, -1))
                 sc = self._scene_desc((key, pk), ps, settings)
+                sc.flags = L.B2R_FLAG_CTX_CLEAN if ps.primed else 0  # every pass leaves its ctx counters zero
+                ps.primed = True
                 sp = st.cuda_stream
                 L.check(lib.b2r_forward_project(C.byref(sc), C.byref(ps.ws), ps.radii.data_ptr(), sp), "b2r_forward_project")
                 L.check(lib.b2r_forward_bin(C.byref(sc), C.byref(ps.ws), sp), "b2r_forward_bin")
@@ -414,7 +424,11 @@ class MergedFivePlan:
                         vs.wait_stream(st)
                     with torch.cuda.stream(vs):
                         color, depth, alpha = ps.img[v]
-                        if views[v].skip_below:  # pre-fill with the scene-only render; the composite overwrites human tiles
+                        if views[v].skip_below and n in ("human", "human_refined"):  # bare background, no depth / alpha
+                            color.copy_(bg_h.view(3, 1, 1).expand_as(color))
+                            depth.zero_()
+                            alpha.zero_()
+                        elif views[v].skip_below:  # pre-fill with the scene-only render; the composite overwrites human tiles
                             vs.wait_event(scene_done)
                             for dst, src in zip(ps.img[v], scene_img):
                                 dst.copy_(src)

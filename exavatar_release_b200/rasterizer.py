@@ -219,9 +219,12 @@ def _forward_impl(settings, means3D, shs, colors, opac, scales, rots, cov, want_
                   ws, ids, scratch, ck = workspace(cap, token)
                   L.check(lib.b2r_forward(C.byref(sc), C.byref(ws), C.byref(out), sptr), "b2r_forward")
                   num = _wait_mirror(st, token, stream)
-                  if num > cap:  # misprediction: redo binning + composite with the exact size
+                  if num > cap:  # misprediction: the whole forward again with the exact size (a forward that was given
+                      # a capacity consumes the tile counters, so the render phase alone cannot be repeated)
+                      token = st.next_token()
                       ws, ids, scratch, ck = workspace(num, token)
-                      L.check(lib.b2r_forward_render(C.byref(sc), C.byref(ws), C.byref(out), sptr), "b2r_forward_render")
+                      L.check(lib.b2r_forward(C.byref(sc), C.byref(ws), C.byref(out), sptr), "b2r_forward")
+                      num = _wait_mirror(st, token, stream)
               else:
                   ws0 = L.B2RWorkspace(ctx_buf.data_ptr(), ctx_bytes, None, 0, None, 0, st.mirror.data_ptr(), token, None, 0)
                   L.check(lib.b2r_forward_project(C.byref(sc), C.byref(ws0), radii.data_ptr(), sptr), "b2r_forward_project")

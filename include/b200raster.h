@@ -44,6 +44,9 @@ extern "C" {
 /* flags */
 #define B2R_FLAG_NO_TILE_CULL 1u /* keep every tile of the 3-sigma rect (reference list membership, for list parity tests) */
 #define B2R_FLAG_DEBUG 2u        /* reference `debug=True` (module.py:621): the host wrapper syncs and checks after the call */
+#define B2R_FLAG_CTX_CLEAN 4u    /* the ctx buffer's counters are zero: its last use was a b2r_forward / b2r_forward_project
+                                    with dup_capacity > 0 (or b2r_forward_render) of this library, which leave them zero
+                                    again -- the projection then skips its reset launch.  Never set it for a fresh buffer. */
 
 /* Scene description shared by forward and backward: the fields of GaussianRasterizationSettings
  * (module.py:609-622) plus the per-Gaussian inputs of the call (module.py:632-640). */
@@ -203,7 +206,10 @@ size_t b2r_scratch_bytes(int32_t P, int32_t width, int32_t height, uint64_t dup_
 size_t b2r_backward_scratch_bytes(int32_t P);
 size_t b2r_checkpoint_bytes(int32_t width, int32_t height, uint64_t dup_capacity);
 
-/* Phase A: projection, tile counting, tile scan.  Writes radii and B2RStatus.num_dups. */
+/* Phase A: projection, tile counting, tile scan.  Writes radii and B2RStatus.num_dups.  With ws->dup_capacity == 0 it
+ * only counts (two-phase use: size the lists from num_dups, then b2r_forward_render).  With a capacity it also prepares
+ * the binning (b2r_forward_bin may follow directly); if that capacity then turns out too small (B2RStatus.overflow), run
+ * the whole forward again with more room -- the tile counters are consumed. */
 int b2r_forward_project(const B2RScene* scene, const B2RWorkspace* ws, int32_t* radii, void* stream);
 /* Phase B: duplicate-with-keys, per-tile sort, forward composite (needs phase A on the same ws). */
 int b2r_forward_render(const B2RScene* scene, const B2RWorkspace* ws, const B2RForwardOutputs* out, void* stream);
