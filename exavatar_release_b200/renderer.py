@@ -20,8 +20,48 @@ from .rasterizer import GaussianRasterizationSettings, GaussianRasterizer
 from .sh import sh_to_rgb
 
 
+# Camera setup of CUDA-resident camera parameters.  The reference evaluates module.py:604-613 on the device: ~35 tiny
+# kernels and five device->host synchronisations per render (float(torch.tan(.)), math.tan(float(.)), .inverse()), i.e.
+# the host waits for everything the GPU still has queued, five times per render, 25 times per training frame.  The
+# arithmetic is 16 floats of input, so this mirror fetches them with ONE packed copy, evaluates the same functions of
+# camera.py on the CPU (where they are pinned bit for bit on the reference's own output, tests/test_golden.py) and
+# uploads the three results with one packed copy.  The five renders of a frame share the camera (model.py:130-162):
+# results are cached per camera -- the entry keeps the caller's tensors alive, so a storage address can never be seen
+# with different contents, and an in-place update bumps the version and misses.
+_CAM_CACHE = {}
+_CAM_CACHE_MAX = 8
+
+
+def _device_camera(img_shape, cam_param):
+    keys = ("R", "t", "focal", "princpt")
+    ts = [cam_param[k] for k in keys]
+    key = tuple((t.data_ptr(), t._version, tuple(t.shape), t.dtype) for t in ts) + (int(img_shape[0]), int(img_shape[1]))
+    hit = _CAM_CACHE.get(key)
+    if hit is not None:
+        return hit[1]
+    dev = ts[0].device
+    packed = torch.cat([t.reshape(-1).float() for t in ts]).cpu()  # one kernel, one copy, one synchronisation
+    host = {"R": packed[0:9].view(3, 3), "t": packed[9:12], "focal": packed[12:14], "princpt": packed[14:16]}
+    fov = get_fov(host["focal"], host["princpt"], img_shape)
+    view = get_view_matrix(host["R"], host["t"]).permute(1, 0)
+    proj = get_proj_matrix(host["focal"], host["princpt"], img_shape, 0.01, 100, 1.0).permute(1, 0)
+    full = torch.mm(view, proj)
+    campos = view.inverse()[3, :3]
+    up = torch.cat((view.reshape(-1), full.reshape(-1), campos.reshape(-1))).to(dev)
+    out = (up[0:16].view(4, 4), up[16:32].view(4, 4), up[32:35], float(torch.tan(fov[0] / 2)), float(torch.tan(fov[1] / 2)))
+    if len(_CAM_CACHE) >= _CAM_CACHE_MAX:
+        _CAM_CACHE.pop(next(iter(_CAM_CACHE)))
+    _CAM_CACHE[key] = (ts, out)  # `ts` held on purpose: pins the storage the key refers to
+    return out
+
+
 def render_settings(img_shape, cam_param, bg, settings_cls=GaussianRasterizationSettings):
     """module.py:604-622: fov, transposed view / full-projection matrices, camera position, settings tuple."""
+    if cam_param["R"].is_cuda:
+        view_matrix, full_proj_matrix, cam_pos, tanx, tany = _device_camera(img_shape, cam_param)
+        return settings_cls(image_height=img_shape[0], image_width=img_shape[1], tanfovx=tanx, tanfovy=tany, bg=bg,
+                            scale_modifier=1.0, viewmatrix=view_matrix, projmatrix=full_proj_matrix, sh_degree=0,
+                            campos=cam_pos, prefiltered=False, debug=False)
     fov = get_fov(cam_param["focal"], cam_param["princpt"], img_shape)
     view_matrix = get_view_matrix(cam_param["R"], cam_param["t"]).permute(1, 0)
     proj_matrix = get_proj_matrix(cam_param["focal"], cam_param["princpt"], img_shape, 0.01, 100, 1.0).permute(1, 0)
