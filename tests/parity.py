@@ -6,7 +6,9 @@ Every comparison of a CUDA result `x` with the oracle's `y` goes through `compar
   * measures -- and reports -- how tight the match actually is: max and 99.9-percentile error on the unflagged AND on
     the flagged set (units of max|y|), the flagged fraction, and the per-element relative error
     |x-y| / max(|y|, floor) (floor: 1e-3 absolute for images, 1e-2 * max|y| for gradient tensors),
-  * holds the flagged set to explicit bounds as well (rare violations, each bounded).
+  * holds the flagged set to explicit bounds as well (rare violations, each bounded by 5e-3 * max|y|), and the
+    99.9-percentile of the unflagged error to 1e-5 -- measured on the B200: unflagged max ~1e-6, flagged max <= 2e-3
+    (profiles/r02_parity_report.jsonl); the 1e-4 bound of north_star is met with two orders of magnitude to spare.
 `contributor_report()` counts the pixels whose last contributor (the Gaussian id behind `n_contrib`) differs from the
 oracle's -- SURVEY section 8c asks for that count; it is expected to be 0 outside threshold cases.
 
@@ -39,7 +41,7 @@ def _pct(a: np.ndarray, q: float) -> float:
 
 
 def compare(case: str, name: str, x, y, bad=None, *, tol: float = TOL, kind: str = "grad", max_flagged_viol: float = 1e-3,
-            loose: float = 0.05, p999_unflagged: float = TOL, assert_it: bool = True) -> dict:
+            loose: float = 5e-3, p999_unflagged: float = 1e-5, assert_it: bool = True) -> dict:
     """kind: "image" (per-element floor 1e-3 absolute) or "grad" (floor 1e-2 * max|y|)."""
     x = np.asarray(x, np.float64)
     y = np.asarray(y, np.float64)

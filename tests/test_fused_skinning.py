@@ -109,6 +109,52 @@ def test_fused_skinning_matches_the_unfused_path(world):
     assert float(a["A"].grad[:, 3, :].abs().max()) == 0.0 and float(b["A"].grad[:, 3, :].abs().max()) == 0.0
 
 
+@pytest.mark.gpu
+@pytest.mark.parametrize("only_posed", [False, True])
+def test_posed_positions_of_the_fused_path_are_differentiable(only_posed):
+    """ExAvatar reads the posed mean_3d outside the rasteriser too (face_mesh_renderer, avatar/main/model.py:172-173; the
+    cat(scene.detach(), human) renders, model.py:117-125).  A loss that touches `posed` must reach xyz, the joint
+    transforms and the translation through the fused path exactly as through the unfused ops -- for Gaussians the render
+    culled as well, and also when the image is not used at all."""
+    from exavatar_release_b200 import rasterizer as RZ
+    dev = torch.device("cuda:0")
+    H, W = 96, 128
+    _, human, _ = make_population_assets("T1", seed=0, device=dev)
+    P, J = human["mean_3d"].shape[0], 55
+    cam = look_at_cam_param(7.0, (H, W), device=dev)
+    st = render_settings((H, W), cam, torch.tensor([0.2, 0.4, 0.9], device=dev))
+    w, A, trans = _rig(P, J, torch.float32, dev)
+    xyz0 = human["mean_3d"] @ cam["R"].t() + cam["t"].view(1, 3)
+    xyz0[:50, 2] -= 100.0  # behind the camera after posing: culled by the render, still read by the second loss term
+    gi = make_grad_image("T1", 2).to(dev)
+    gp = torch.randn(P, 3, generator=torch.Generator().manual_seed(3)).to(dev)
+
+    def leaves():
+        return {"xyz": xyz0.clone().requires_grad_(), "A": A.clone().requires_grad_(), "trans": trans.clone().requires_grad_()}
+
+    def loss_of(img, posed):
+        extra = (posed * gp).sum()
+        return extra if only_posed else (img * gi).sum() + extra
+
+    a = leaves()
+    posed_a = lbs_reference(a["xyz"], w, a["A"], a["trans"], cam["R"], cam["t"])
+    img_a = RZ.GaussianRasterizer(st)(means3D=posed_a, means2D=torch.zeros(P, 3, device=dev), opacities=human["opacity"],
+                                      colors_precomp=human["rgb"], scales=human["scale"], rotations=human["rotation"])[0]
+    loss_of(img_a, posed_a).backward()
+    b = leaves()
+    img_b, rad_b, _, _, posed_b = RZ.SkinnedGaussianRasterizer(st)(b["xyz"], w, b["A"], b["trans"], cam["R"], cam["t"],
+                                                                  torch.zeros(P, 3, device=dev), human["opacity"],
+                                                                  human["rgb"], human["scale"], human["rotation"])
+    assert posed_b.requires_grad
+    loss_of(img_b, posed_b).backward()
+    torch.cuda.synchronize()
+    assert int((rad_b[:50] == 0).sum()) == 50 and int((rad_b > 0).sum()) > P // 2
+    for k in ("xyz", "A", "trans"):
+        assert float(a[k].grad.abs().max()) > 0, k
+        _close(k, b[k].grad, a[k].grad)
+    assert float(b["xyz"].grad[:50].abs().max()) > 0  # the culled Gaussians received the posed-position gradient
+
+
 def test_host_helpers_of_the_skinning_backward():
     """`_inv3` (graph-capturable 3x3 inverse) and `_tall_skinny_tn` (W^T G as a batched GEMM) against the plain ops."""
     from exavatar_release_b200.rasterizer import _inv3, _tall_skinny_tn
