@@ -596,19 +596,21 @@ def bench_five(env, args, wl, wl_key):
                                "(loss.mean(), train.py:43); gradient bucket + densify statistics all-reduced"}
 
     # ---- end to end through the public API with host buffers ----
-    e2e, e2e_eager = None, None
+    e2e, e2e_eager, e2e_merged = None, None, None
     if not args.no_e2e:
-        e2e, e2e_eager = e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_a, max(caps.values()),
-                                  collectives if world > 1 else None)
+        caps_merged = caps if "A" in caps else {"A": int(need["scene_human"] * 1.1) + 4096,
+                                                 "B": int(need["scene_human_refined"] * 1.1) + 4096}
+        e2e, e2e_eager, e2e_merged = e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_a,
+                                              max(caps.values()), caps_merged, collectives if world > 1 else None)
 
     extra = {"cuda_graph": graph is not None, "dup_capacity": caps, "engine": engine_kind, "lanes": S,
              "streams": engine.describe() + f"; {S} training frame(s) in flight"}
     return {"value": fps, "ms_per_step": ms_total / K, "clocks": clk, "launches": int(launches), "roofline": roofline,
-            "e2e": e2e, "e2e_eager": e2e_eager, "strong_scaling": strong, "collective": coll, "wall": wall, "config": extra,
-            "warmup": Wm}
+            "e2e": e2e, "e2e_eager": e2e_eager, "e2e_merged": e2e_merged, "strong_scaling": strong, "collective": coll,
+            "wall": wall, "config": extra, "warmup": Wm}
 
 
-def e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_a, cap, collectives):
+def e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_a, cap, caps_merged, collectives):
     """ExAvatar's training frame through the PUBLIC API with pinned host buffers (see module docstring)."""
     from exavatar_release_b200 import rasterizer as RZ
     from exavatar_release_b200.renderer import GaussianRenderer
@@ -630,6 +632,14 @@ def e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_
     S = max(1, min(4, F))  # frames in flight on the autograd path (each frame: five renders in sequence on its lane)
     cat = lambda a, b: {k: torch.cat((a[k].detach(), b[k])) for k in a}  # model.py:117-125
 
+    fused = []  # one TrainingFrameRenderer per lane (built lazily for the e2e_merged leg)
+
+    def frame_loss_fused(lv, f, tgt, lane):
+        out = fused[lane](lv["scene"], lv["human"], lv["refined"], cams[f], bg_r, raster_settings=st_w[f],
+                          raster_settings_human=st_r[f])
+        imgs = [out[r]["img"] for r in FIVE]
+        return sum(torch.nn.functional.l1_loss(im, tgt) for im in imgs), imgs
+
     def frame_loss(lv, f, tgt, use_cached_settings):
         kw_w = {"raster_settings": st_w[f]} if use_cached_settings else {}
         kw_r = {"raster_settings": st_r[f]} if use_cached_settings else {}
@@ -645,7 +655,7 @@ def e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_
     h2d_s, d2h_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
     lane_s = [torch.cuda.Stream(dev) for _ in range(S)]
 
-    def body(use_cached_settings=True):
+    def body(use_cached_settings=True, use_fused=False):
         cur = torch.cuda.current_stream(dev)
         for st_ in lane_s:
             st_.wait_stream(cur)
@@ -672,7 +682,7 @@ def e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_
             fs, lv = lane_s[f % S], leaves[f % S]
             with torch.cuda.stream(fs):
                 fs.wait_event(ev_t[f])
-                loss, imgs = frame_loss(lv, f, tgts[f], use_cached_settings)
+                loss, imgs = frame_loss_fused(lv, f, tgts[f], f % S) if use_fused else frame_loss(lv, f, tgts[f], use_cached_settings)
                 loss.backward()
                 losses.append(loss.detach().reshape(1))
                 keep_alive.append((imgs, loss))
@@ -748,6 +758,55 @@ def e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_
                                                                   if graph is not None else "eager, copies on side streams"),
            "steps": ke, "lanes": S}
 
+    # ---- the same step through TrainingFrameRenderer: one autograd call per frame, two merged passes ----
+    merged = None
+    try:
+        from exavatar_release_b200 import TrainingFrameRenderer
+        for _ in range(S):
+            fused.append(TrainingFrameRenderer(wl.n_scene, wl.n_avatar, (H, Wd), dev, caps_merged))
+        side = torch.cuda.Stream(dev)
+        side.wait_stream(torch.cuda.current_stream(dev))
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                body(use_fused=True)
+                torch.cuda.synchronize(dev)
+                keep_alive.clear()
+        torch.cuda.current_stream(dev).wait_stream(side)
+        torch.cuda.synchronize(dev)
+        mgraph = None
+        if not args.no_graph:
+            mgraph = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(mgraph):
+                body(use_fused=True)
+
+        def mstep():
+            if mgraph is not None:
+                mgraph.replay()
+            else:
+                body(use_fused=True)
+                torch.cuda.synchronize(dev)
+                keep_alive.clear()
+            if collectives is not None:
+                collectives()
+
+        for _ in range(3):
+            mstep()
+        ms_m, _, _ = env.timed(mstep, ke)
+        if any(fr.overflowed() for fr in fused):
+            raise RuntimeError("fixed duplicate capacity overflowed")
+        merged = {"value": world * F * ke / (ms_m * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                  "steps": ke, "lanes": S,
+                  "api": "TrainingFrameRenderer (exavatar_release_b200/fused.py): the five renders of model.py:117-162 as one "
+                         "autograd call per frame (two merged projection+binning passes, five views), same losses, copies "
+                         "and graph capture as `e2e`; needs the caller to replace model.py:117-162 (INTEGRATION.md)"}
+        del mgraph
+        fused.clear()
+        keep_alive.clear()
+        torch.cuda.empty_cache()
+    except Exception as exc:  # an extra leg: report, do not fail the bench
+        print(f"bench.py: e2e_merged leg failed ({type(exc).__name__}: {exc})", file=sys.stderr)
+        torch.cuda.synchronize(dev)
+
     # ---- eager: the unmodified reference call shape, adaptive capacity, no graph ----
     eager = None
     if not args.no_eager:
@@ -770,7 +829,7 @@ def e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_
                  "host_ms_per_render": ms_g / (kk * F * 5),
                  "api": "GaussianRenderer.forward(assets, img_shape, cam_param, bg) exactly as module.py:592 (camera matrices "
                         "rebuilt per call, no cached settings), adaptive duplicate capacity, no CUDA graph"}
-    return e2e, eager
+    return e2e, eager, merged
 
 
 # ---------------------------------------------------------------------------------------------------------------
@@ -1078,7 +1137,7 @@ def bench_single(env, args, wl, wl_key, brief=False):
                "steps": ke}
 
     return {"value": fps, "ms_per_step": ms_total / K, "clocks": clk, "launches": int(launches), "roofline": roofline,
-            "e2e": e2e, "e2e_eager": None, "strong_scaling": None, "collective": None, "wall": wall,
+            "e2e": e2e, "e2e_eager": None, "e2e_merged": None, "strong_scaling": None, "collective": None, "wall": wall,
             "config": {"cuda_graph": graph is not None, "dup_capacity": cap, "lanes": S}, "warmup": Wm}
 
 
@@ -1113,7 +1172,8 @@ def run_b200(args):
                 "warmup": res["warmup"], "ms_per_step": res["ms_per_step"], "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": cfg, "clocks": res["clocks"],
                 "e2e": res["e2e"], "gpu_launches": res["launches"], "roofline": res["roofline"], "cpu_baseline": cpu,
-                "e2e_eager": res["e2e_eager"], "strong_scaling": res["strong_scaling"], "collective": res["collective"],
+                "e2e_eager": res["e2e_eager"], "e2e_merged": res["e2e_merged"], "strong_scaling": res["strong_scaling"],
+                "collective": res["collective"],
                 "single_render": single, "wall_s_timed_region": res["wall"]}
         print(json.dumps(line), flush=True)
     if env.world > 1:

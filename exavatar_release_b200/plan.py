@@ -378,6 +378,13 @@ class MergedFivePlan:
                 buf[: self.Ps].copy_(scene_assets[k].reshape(self.Ps, -1))
 
     def _scene_desc(self, key, ps, settings):
+        """B2RScene of a pass for one camera; cached under `key` (the settings' tensors are then kept alive), or built
+        afresh when key[0] is None (a caller with a new camera every frame)."""
+        if key[0] is None:
+            sc, keep = _make_scene(settings, ps.cat["mean_3d"], None, ps.cat["rgb"], ps.cat["opacity"], ps.cat["scale"],
+                                   ps.cat["rotation"], None, 0)
+            ps.last_scene = (sc, keep)  # alive until the pass is used again
+            return sc
         if key not in self._scenes:
             sc, keep = _make_scene(settings, ps.cat["mean_3d"], None, ps.cat["rgb"], ps.cat["opacity"], ps.cat["scale"],
                                    ps.cat["rotation"], None, 0)
@@ -461,6 +468,104 @@ class MergedFivePlan:
         if not serial:
             for pk in self.passes:
                 cur.wait_stream(self.pass_streams[pk])
+
+    # ---- the same frame in two halves (forward now, backward when the caller's gradients exist): fused.py ----
+    def forward_frame(self, key, settings, settings_human_bg, scene, human, refined) -> None:
+        """Forward of the five renders; images in `render_outputs()`, per-pixel state and checkpoints stay in the plan
+        until `backward_frame` (so the plan must not start another frame in between)."""
+        lib = self.lib
+        cur = torch.cuda.current_stream(self.device)
+        bg_h = _f32c(settings_human_bg.bg.to(self.device), "bg")
+        self._keep.append(bg_h)
+        del self._keep[:-64]
+        scene_img = self.passes["A"].img[0]
+        scene_done = torch.cuda.Event()
+        self._pending = {}
+        for pk, names in self.VIEWS.items():
+            ps = self.passes[pk]
+            st = self.pass_streams[pk]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                src = human if pk == "A" else refined
+                for k, buf in ps.cat.items():
+                    buf[self.Ps:].copy_(src[k].reshape(self.Ph, -1))
+                sc = self._scene_desc((key, pk), ps, settings)
+                sc.flags = L.B2R_FLAG_CTX_CLEAN if ps.primed else 0
+                ps.primed = True
+                sp = st.cuda_stream
+                L.check(lib.b2r_forward_project(C.byref(sc), C.byref(ps.ws), ps.radii.data_ptr(), sp), "b2r_forward_project")
+                L.check(lib.b2r_forward_bin(C.byref(sc), C.byref(ps.ws), sp), "b2r_forward_bin")
+                views = [self._view(ps, v, n, bg_h if n in ("human", "human_refined") else None) for v, n in enumerate(names)]
+                self._pending[pk] = (sc, views)
+                for v, n in enumerate(names):
+                    vs = ps.streams[v]
+                    vs.wait_stream(st)
+                    with torch.cuda.stream(vs):
+                        color, depth, alpha = ps.img[v]
+                        if views[v].skip_below and n in ("human", "human_refined"):
+                            color.copy_(bg_h.view(3, 1, 1).expand_as(color))
+                            depth.zero_()
+                            alpha.zero_()
+                        elif views[v].skip_below:
+                            vs.wait_event(scene_done)
+                            for dst, src_ in zip(ps.img[v], scene_img):
+                                dst.copy_(src_)
+                        out = L.B2RForwardOutputs(color.data_ptr(), depth.data_ptr(), alpha.data_ptr(), ps.radii.data_ptr())
+                        L.check(lib.b2r_forward_composite(C.byref(sc), C.byref(ps.ws), C.byref(views[v]), C.byref(out),
+                                                          vs.cuda_stream), "b2r_forward_composite")
+                        if n == "scene":
+                            scene_done.record(vs)
+                for v in range(len(names)):
+                    st.wait_stream(ps.streams[v])
+        for pk in self.passes:
+            cur.wait_stream(self.pass_streams[pk])
+
+    def backward_frame(self, g_colors: Dict[str, Optional[torch.Tensor]], grads_A: Dict[str, torch.Tensor],
+                       grads_B: Dict[str, torch.Tensor], g_depths: Optional[Dict[str, torch.Tensor]] = None,
+                       g_alphas: Optional[Dict[str, torch.Tensor]] = None, accumulate: bool = False,
+                       densify: Optional[Dict[str, torch.Tensor]] = None) -> None:
+        """Backward of the frame `forward_frame` rendered.  g_colors[name] = dL/dimage of a render, or None when the render
+        was not used downstream.  grads_A / grads_B: `_views_of`-style dicts with P / P_human rows (pass A: scene rows then
+        human rows; pass B: refined rows)."""
+        lib = self.lib
+        cur = torch.cuda.current_stream(self.device)
+        for pk, names in self.VIEWS.items():
+            ps = self.passes[pk]
+            sc, views = self._pending[pk]
+            st = self.pass_streams[pk]
+            st.wait_stream(cur)
+            with torch.cuda.stream(st):
+                for v, n in enumerate(names):
+                    gc, gd, ga = g_colors.get(n), (g_depths or {}).get(n), (g_alphas or {}).get(n)
+                    if gc is None and gd is None and ga is None:
+                        continue  # this render was not used downstream
+                    vs = ps.streams[v]
+                    vs.wait_stream(st)
+                    with torch.cuda.stream(vs):
+                        if gc is None:
+                            gc = torch.zeros(3, self.H, self.W, dtype=torch.float32, device=self.device)
+                        a = L.B2RBackwardArgs(_ptr(gc), _ptr(gd), _ptr(ga))
+                        a.flags = L.B2R_BWD_SCRATCH_ZEROED
+                        a.first_row = self.first_row[n]
+                        L.check(lib.b2r_backward_composite(C.byref(sc), C.byref(ps.ws), C.byref(views[v]), C.byref(a),
+                                                           ps.bwd_scratch.data_ptr(), ps.bwd_bytes, vs.cuda_stream),
+                                "b2r_backward_composite")
+                        self._keep.append((gc, gd, ga))
+                for v in range(len(names)):
+                    st.wait_stream(ps.streams[v])
+                g = grads_A if pk == "A" else grads_B
+                a = L.B2RBackwardArgs(None, None, None, _ptr(g["means3D"]), _ptr(g["means2D"]), None, _ptr(g["colors"]),
+                                      _ptr(g["opacities"]), _ptr(g["scales"]), _ptr(g["rotations"]), None)
+                a.flags = (L.B2R_BWD_ACCUMULATE if accumulate else 0) | L.B2R_BWD_SCRATCH_ZEROED
+                a.first_row = 0 if pk == "A" else self.Ps
+                if pk == "A" and densify is not None:
+                    a.densify_grad_accum, a.densify_count = _ptr(densify.get("grad_accum")), _ptr(densify.get("count"))
+                    a.densify_radius_max = _ptr(densify.get("radius_max"))
+                    a.densify_rows = self.Ps
+                L.check(lib.b2r_backward_project(C.byref(sc), C.byref(ps.ws), C.byref(a), ps.bwd_scratch.data_ptr(),
+                                                 ps.bwd_bytes, st.cuda_stream), "b2r_backward_project")
+        for pk in self.passes:
+            cur.wait_stream(self.pass_streams[pk])
 
     def render_outputs(self, render: str):
         pk = "A" if render in self.VIEWS["A"] else "B"
