@@ -43,6 +43,12 @@ def _stale() -> bool:
 
 
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
+    # B2R_LIB_OUT + B2R_NVCC_EXTRA: a tuning variant of the same library next to the product one (load it with B2R_LIB)
+    global LIB
+    variant = os.environ.get("B2R_LIB_OUT")
+    if variant:
+        LIB = os.path.abspath(variant)
+        force = True
     if not force and not _stale():
         return LIB
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
@@ -50,7 +56,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     # one object per translation unit, compiled in parallel (no relocatable device code: kernels never call across
     # files), then one link -- a full rebuild takes as long as the slowest file instead of the sum
     from concurrent.futures import ThreadPoolExecutor
-    objdir = os.path.join(PKG, "build")
+    objdir = os.path.join(PKG, "build") if not variant else os.path.join(os.path.dirname(LIB), "obj_" + os.path.basename(LIB))
     os.makedirs(objdir, exist_ok=True)
     flags = [f for f in NVCC_FLAGS if f != "--shared"]
     srcs = sources()

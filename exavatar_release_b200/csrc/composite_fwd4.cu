@@ -175,7 +175,10 @@ constexpr int FL_THREADS = 64;
 constexpr int FL_BATCH = 128;
 static_assert(SEG % FL_BATCH == 0, "checkpoint cuts fall on batch boundaries");
 
-__global__ void __launch_bounds__(FL_THREADS) composite_fwd_kernel(const B2RScene sc, const Ctx cx,
+#ifndef F4_MIN_BLOCKS
+#define F4_MIN_BLOCKS 1  // tuning hook: 16 forces <= 64 registers (measured, profiles/r02_notes.md)
+#endif
+__global__ void __launch_bounds__(FL_THREADS, F4_MIN_BLOCKS) composite_fwd_kernel(const B2RScene sc, const Ctx cx,
                                                                           const B2RForwardOutputs out, const int vec_ok) {
   __shared__ F4Stage stage_raw;          // used as two 128-entry halves: [0,128) and [128,256) of every array
   __shared__ F4Queue queue[2];
