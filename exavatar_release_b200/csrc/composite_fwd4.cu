@@ -29,7 +29,10 @@
 
 namespace b2r {
 
-constexpr int F4_BATCH = SEG;  // capacity of the two-half staging buffer (2 x 128 entries)
+#ifndef FL_BATCH_N
+#define FL_BATCH_N 128  // entries staged per batch (tuning hook; 64 measured in profiles/r02_notes.md)
+#endif
+constexpr int F4_BATCH = 2 * FL_BATCH_N;  // capacity of the two-half staging buffer
 constexpr int F4_GROUP = 4;    // splats blended per trip of the hit loop (their evaluations overlap: ILP 4)
 constexpr int F4_CQ = 36;      // survivor queue: <= 3 left over + 32 new per chunk (+ pad)
 
@@ -172,7 +175,7 @@ __device__ __forceinline__ void write_outputs(const B2RScene& sc, const Ctx& cx,
 }
 
 constexpr int FL_THREADS = 64;
-constexpr int FL_BATCH = 128;
+constexpr int FL_BATCH = FL_BATCH_N;
 static_assert(SEG % FL_BATCH == 0, "checkpoint cuts fall on batch boundaries");
 
 #ifndef F4_MIN_BLOCKS
@@ -250,9 +253,9 @@ __global__ void __launch_bounds__(FL_THREADS, F4_MIN_BLOCKS) composite_fwd_kerne
       cull_and_blend(stage_raw, half + idx, idx < count, b * FL_BATCH + idx + 1, cw, fill, S, rx0, ry0, rx1, ry1, pxf, pyf);
       warp_live = __any_sync(0xffffffffu, S.T > 0.f);
     }
-    if (ck && (b & 1) && b + 1 < nb) {  // cut at list position 128 (b+1), a multiple of 256: the state must be exact there
+    if (ck && ((b + 1) * FL_BATCH) % SEG == 0 && b + 1 < nb) {  // a cut (multiple of 256): the state must be exact there
       flush_queue(cw, fill, S, pxf, pyf);
-      if (inside) store_checkpoint(ck + (size_t)(b >> 1) * CK_REC_FLOATS, pix_in_tile, S);
+      if (inside) store_checkpoint(ck + (size_t)((b + 1) * FL_BATCH / SEG - 1) * CK_REC_FLOATS, pix_in_tile, S);
     }
   }
   flush_queue(cw, fill, S, pxf, pyf);
