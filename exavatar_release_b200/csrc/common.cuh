@@ -43,6 +43,7 @@ enum { CLS_N_LARGE = 0,   // tiles with >= 2048 entries (sorted in chunks)
        CLS_TOTAL_SEGS = 4,  // segments of the multi-segment tiles
        CLS_N_GE1024 = 5,    // tiles with >= 1024 entries
        CLS_VIS_ACC = 6,     // visible-Gaussian accumulator of the projection kernel (published to B2RStatus by the scan)
+       CLS_SCAN_FINAL = 7,  // 1 once a final scan has consumed the tile counters of the current projection
        CLS_COUNT = 8 };
 constexpr size_t ALIGN = 256;
 __host__ __device__ inline size_t align_up(size_t v) { return (v + ALIGN - 1) / ALIGN * ALIGN; }

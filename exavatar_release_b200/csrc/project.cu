@@ -183,6 +183,7 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
                             g.g0.w, g.g1.x, g.g1.w, 0u, 0u, (sc.flags & B2R_FLAG_NO_TILE_CULL) != 0, sc.width, sc.height,
                             [&](int tx, int ty, uint32_t, uint32_t) { atomicAdd(tile_count + ty * gx + tx, 1u); });
   }
+  if (blockIdx.x == 0 && threadIdx.x == 0) cx.classes[CLS_SCAN_FINAL] = 0u;  // new counts: no final scan yet
   const unsigned vis = __ballot_sync(0xffffffffu, visible);
   if ((threadIdx.x & 31) == 0 && vis) atomicAdd(&cx.classes[CLS_VIS_ACC], (uint32_t)__popc(vis));
   if (aggregate) {
@@ -199,7 +200,11 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
 // `final`: this scan's ranges are the ones the binning will use (a duplicate capacity was given), so the per-tile
 // counters are consumed: the kernel leaves them -- and the other accumulators of the ctx -- zero for the next render,
 // which can then skip status_reset_kernel (B2R_FLAG_CTX_CLEAN).
+// `final` = 2: the re-scan of b2r_forward_render.  If the projection phase already ran a final scan (it was given a
+// capacity), the counters are gone and its ranges stand: nothing to do (B2RStatus.overflow still tells the caller when
+// that capacity was too small).
 __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx, const int final) {
+  if (final == 2 && cx.classes[CLS_SCAN_FINAL] != 0u) return;
   __shared__ uint64_t warp_sums[32];
   __shared__ uint64_t carry_s;
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
@@ -338,7 +343,10 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx, const int
   if (threadIdx.x == 0) {
     const uint64_t total = carry_s;
     cx.status->num_visible = cx.classes[CLS_VIS_ACC];
-    if (final) cx.classes[CLS_VIS_ACC] = 0u;
+    if (final) {
+      cx.classes[CLS_VIS_ACC] = 0u;
+      cx.classes[CLS_SCAN_FINAL] = 1u;
+    }
     cx.status->consumed_fwd = 0;
     cx.status->consumed_bwd = 0;
     cx.status->num_dups = total;
@@ -369,6 +377,7 @@ __global__ void status_reset_kernel(const Ctx cx) {
     s->consumed_fwd = 0;
     s->consumed_bwd = 0;
     cx.classes[CLS_VIS_ACC] = 0u;
+    cx.classes[CLS_SCAN_FINAL] = 0u;
   }
 }
 
@@ -399,7 +408,7 @@ int launch_project(const B2RScene& sc, const Ctx& cx, int32_t* radii, cudaStream
 
 void launch_tile_scan(const Ctx& cx, cudaStream_t st) {
   ProfScope p(K_TILE_SCAN, st);
-  launch_k(tile_scan_kernel, 1, 1024, 0, st, true, cx, 1);
+  launch_k(tile_scan_kernel, 1, 1024, 0, st, true, cx, 2);
 }
 
 int launch_mark_visible(int P, const float* means3D, const float* view, uint8_t* present, cudaStream_t st) {

@@ -211,7 +211,9 @@ size_t b2r_checkpoint_bytes(int32_t width, int32_t height, uint64_t dup_capacity
  * the binning (b2r_forward_bin may follow directly); if that capacity then turns out too small (B2RStatus.overflow), run
  * the whole forward again with more room -- the tile counters are consumed. */
 int b2r_forward_project(const B2RScene* scene, const B2RWorkspace* ws, int32_t* radii, void* stream);
-/* Phase B: duplicate-with-keys, per-tile sort, forward composite (needs phase A on the same ws). */
+/* Phase B: duplicate-with-keys, per-tile sort, forward composite (needs phase A on the same ws).  After a count-only
+ * phase A it re-derives the per-tile ranges for ws->dup_capacity; after a phase A that was given a capacity it uses the
+ * ranges that phase prepared (same capacity expected). */
 int b2r_forward_render(const B2RScene* scene, const B2RWorkspace* ws, const B2RForwardOutputs* out, void* stream);
 /* Both phases with a capacity chosen up front. */
 int b2r_forward(const B2RScene* scene, const B2RWorkspace* ws, const B2RForwardOutputs* out, void* stream);

@@ -395,6 +395,53 @@ def test_accumulate_mode_sums_frames(dev):
     assert plan.status()["overflow"] == 0
 
 
+def test_split_entry_points_agree_with_the_one_call_forward(dev):
+    """b2r_forward == count-only b2r_forward_project + b2r_forward_render == b2r_forward_project (with the capacity) +
+    b2r_forward_render == ... + b2r_forward_bin + b2r_forward_composite(view = NULL); also with a clean-flagged ctx."""
+    import ctypes as C
+    from exavatar_release_b200 import _lib as L
+    from exavatar_release_b200.plan import FramePlan
+    rz = RZ()
+    wl = WORKLOADS["T1"]
+    a = {k: v.to(dev) for k, v in make_assets("T1", seed=3).items()}
+    P = a["mean_3d"].shape[0]
+    st = workload_settings("T1", yaw=-5.0, device=dev, settings_cls=rz.GaussianRasterizationSettings)
+    plan = FramePlan(P, wl.width, wl.height, 1_000_000, dev)
+    sc = plan.scene(0, st, a)
+    lib, sp = plan.lib, torch.cuda.current_stream(dev).cuda_stream
+    plan.forward(sc)
+    torch.cuda.synchronize()
+    ref = (plan.color.clone(), plan.depth.clone(), plan.alpha.clone(), plan.radii.clone())
+    ref_ids = plan.ids.clone()
+
+    def check(tag):
+        torch.cuda.synchronize()
+        assert plan.status()["overflow"] == 0, tag
+        for x, y in zip((plan.color, plan.depth, plan.alpha, plan.radii), ref):
+            assert torch.equal(x, y), tag
+        n = plan.status()["num_dups"]
+        assert torch.equal(plan.ids[:n], ref_ids[:n]), tag
+
+    for flags in (0, L.B2R_FLAG_CTX_CLEAN):  # every sequence below leaves the counters clean again
+        sc.flags = flags
+        plan.color.zero_()
+        ws0 = L.B2RWorkspace(plan.ctx_buf.data_ptr(), plan.ctx_bytes, None, 0, None, 0, None, 0, None, 0)
+        L.check(lib.b2r_forward_project(C.byref(sc), C.byref(ws0), plan.radii.data_ptr(), sp), "project(count only)")
+        L.check(lib.b2r_forward_render(C.byref(sc), C.byref(plan.ws), C.byref(plan.out), sp), "render")
+        check(f"count-only project + render, flags {flags}")
+        sc.flags = L.B2R_FLAG_CTX_CLEAN
+        plan.color.zero_()
+        L.check(lib.b2r_forward_project(C.byref(sc), C.byref(plan.ws), plan.radii.data_ptr(), sp), "project(capacity)")
+        L.check(lib.b2r_forward_render(C.byref(sc), C.byref(plan.ws), C.byref(plan.out), sp), "render")
+        check("project with capacity + render")
+        plan.color.zero_()
+        L.check(lib.b2r_forward_project(C.byref(sc), C.byref(plan.ws), plan.radii.data_ptr(), sp), "project(capacity)")
+        L.check(lib.b2r_forward_bin(C.byref(sc), C.byref(plan.ws), sp), "bin")
+        L.check(lib.b2r_forward_composite(C.byref(sc), C.byref(plan.ws), None, C.byref(plan.out), sp), "composite")
+        check("project + bin + composite")
+    sc.flags = 0
+
+
 def test_cuda_graph_replay_matches_eager(dev):
     from exavatar_release_b200.plan import FramePlan, grad_bucket
     rz = RZ()
