@@ -425,7 +425,7 @@ def make_five_engine(kind, Ps, Ph, W, H, caps, dev):
 def bench_five(env, args, wl, wl_key):
     from exavatar_release_b200 import rasterizer as RZ
     from exavatar_release_b200.renderer import GaussianRenderer, render_settings
-    from exavatar_release_b200.sharding import shard_frames
+    from exavatar_release_b200.sharding import reduce_densify_stats, shard_frames
     dev, lib, world, rank = env.dev, env.lib, env.world, env.rank
     F, K, Wm = args.frames, args.steps, max(args.warmup, 3)
     H, Wd = wl.height, wl.width
@@ -506,9 +506,7 @@ def bench_five(env, args, wl, wl_key):
         """one gradient all-reduce per step + the small densification-statistics reduction
         (module.py:111-113,155-157: xyz_grad_accum sum, track_cnt sum, radius_max max)."""
         env.dist.all_reduce(flat)
-        env.dist.all_reduce(stats["grad_accum"])
-        env.dist.all_reduce(stats["count"])
-        env.dist.all_reduce(stats["radius_max"], op=env.dist.ReduceOp.MAX)
+        reduce_densify_stats(stats)
 
     def step():
         if graph is not None:
@@ -564,9 +562,43 @@ def bench_five(env, args, wl, wl_key):
     Cb = sum(sum(c["bwd"]) for c in cons) / sum(len(c["bwd"]) for c in cons)
     algo = {"composite_fwd": 44.0 * Cf + 24.0 * N + 8.0 * tiles, "composite_bwd": 84.0 * Cb + 20.0 * N}
     frame_kernel_ms = sum(v["ms_avg"] * v["launches"] for v in per_kernel.values()) / (prof_steps * F)
-    roofline = roofline_dict(per_kernel, algo, wl_key + ("/five" if True else ""), {
+    # per-view composite launches of one frame (merged engine): the five launches differ by an order of magnitude in work
+    per_view = None
+    if engine_kind == "merged":
+        from exavatar_release_b200 import _lib as LL
+        peak = float(peaks_and_traffic(wl_key, "composite_fwd")[0].get("hbm_gbs", 6650.0))
+        lib.b2r_profile_enable(1)
+        env.profile_read()
+        per_view, last = {}, {"A": (0, 0), "B": (0, 0)}
+
+        def probe(label):
+            torch.cuda.synchronize(dev)
+            pk_ms = env.profile_read()
+            parts = label.split(":")
+            if len(parts) != 3:
+                return
+            pk, name, which = parts
+            st = engine.passes[pk].status()
+            key = "consumed_fwd" if which == "fwd" else "consumed_bwd"
+            div = LL.CONSUMED_FWD_DIV if which == "fwd" else LL.CONSUMED_BWD_DIV
+            idx = 0 if which == "fwd" else 1
+            c = (st[key] - last[pk][idx]) / div
+            last[pk] = (st[key], last[pk][1]) if which == "fwd" else (last[pk][0], st[key])
+            ms = pk_ms["composite_fwd" if which == "fwd" else "composite_bwd"]["ms_avg"]
+            nbytes = (44.0 * c + 24.0 * N + 8.0 * tiles) if which == "fwd" else (84.0 * c + 20.0 * N)
+            per_view.setdefault(name, {})[which] = {"ms": round(ms, 5), "consumed": c, "algorithmic_bytes": nbytes,
+                                                     "frac": (nbytes / (ms * 1e-3) / 1e9 / peak) if ms > 0 else None}
+
+        engine.set_scene(scene_a)
+        engine.frame(("f", weak_frames[0]), st_w[0], st_r[0], scene_a, human_a, refined_a, g5[weak_frames[0] % 8],
+                     accumulate=False, serial=True, probe=probe)
+        torch.cuda.synchronize(dev)
+        lib.b2r_profile_enable(0)
+    roofline = roofline_dict(per_kernel, algo, wl_key + "/five", {
         "sum_kernel_ms_per_training_frame": frame_kernel_ms, "consumed_fwd_per_render": Cf, "consumed_bwd_per_render": Cb,
-        "dups_needed": need, "note": "per-launch averages over the composite launches of a training frame"})
+        "dups_needed": need, "per_view": per_view,
+        "note": "per-launch averages over the five composite launches of a training frame; three of the five views skip "
+                "the tiles no human Gaussian reaches (see per_view for each launch)"})
 
     # ---- strong scaling (configs[3] literally): global batch of 8 frames over the ranks ----
     strong = None

@@ -400,8 +400,11 @@ class MergedFivePlan:
         return L.B2RView(lo, hi, _ptr(bg), fT.data_ptr(), nc.data_ptr(), ps.ck[v].data_ptr(), ps.ck_bytes, skip, 0)
 
     def frame(self, key, settings, settings_human_bg, scene, human, refined, g_colors: Dict[str, torch.Tensor],
-              accumulate: bool, densify: Optional[Dict[str, torch.Tensor]] = None, serial: bool = False) -> None:
+              accumulate: bool, densify: Optional[Dict[str, torch.Tensor]] = None, serial: bool = False, probe=None) -> None:
+        """`probe(label)` (serial mode): called after every stage -- bench.py reads the in-library profiler there to get
+        per-view kernel times."""
         lib = self.lib
+        probe = probe if (probe is not None and serial) else (lambda label: None)
         cur = torch.cuda.current_stream(self.device)
         bg_h = _f32c(settings_human_bg.bg.to(self.device), "bg")
         self._keep.append(bg_h)
@@ -423,6 +426,7 @@ class MergedFivePlan:
                 sp = st.cuda_stream
                 L.check(lib.b2r_forward_project(C.byref(sc), C.byref(ps.ws), ps.radii.data_ptr(), sp), "b2r_forward_project")
                 L.check(lib.b2r_forward_bin(C.byref(sc), C.byref(ps.ws), sp), "b2r_forward_bin")
+                probe(f"{pk}:bin")
                 views = [self._view(ps, v, n, bg_h if n in ("human", "human_refined") else None) for v, n in enumerate(names)]
                 # forward + backward composite of every view; the views of a pass are independent of each other
                 for v, n in enumerate(names):
@@ -444,12 +448,14 @@ class MergedFivePlan:
                                                           vs.cuda_stream), "b2r_forward_composite")
                         if n == "scene":
                             scene_done.record(vs)
+                        probe(f"{pk}:{n}:fwd")
                         a = L.B2RBackwardArgs(_ptr(g_colors[n]))
                         a.flags = L.B2R_BWD_SCRATCH_ZEROED
                         a.first_row = self.first_row[n]
                         L.check(lib.b2r_backward_composite(C.byref(sc), C.byref(ps.ws), C.byref(views[v]), C.byref(a),
                                                            ps.bwd_scratch.data_ptr(), ps.bwd_bytes, vs.cuda_stream),
                                 "b2r_backward_composite")
+                        probe(f"{pk}:{n}:bwd")
                 if not serial:
                     for v in range(len(names)):
                         st.wait_stream(ps.streams[v])

@@ -62,3 +62,24 @@ def sharded_step(frames: Sequence, frame_grads: Callable[[object, float], Dict[s
     for i in shard_frames(len(frames), rank, world):
         bucket.add_(frame_grads(frames[i], scale))
     return bucket.all_reduce()
+
+
+def reduce_densify_stats(stats: Dict[str, torch.Tensor]) -> Dict[str, torch.Tensor]:
+    """The second, small collective of a sharded step: ExAvatar's densification bookkeeping of the
+    scene Gaussians -- `xyz_grad_accum` and `track_cnt` are SUMS over the frames of the batch, `radius_max` a MAX
+    (avatar/common/nets/module.py:111-113, 155-157; avatar/main/model.py:283-285) -- so every replica prunes and
+    densifies from the statistics of the whole batch.  Keys: 'grad_accum', 'count', 'radius_max' (in place)."""
+    if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(stats["grad_accum"], op=dist.ReduceOp.SUM)
+        dist.all_reduce(stats["count"], op=dist.ReduceOp.SUM)
+        dist.all_reduce(stats["radius_max"], op=dist.ReduceOp.MAX)
+    return stats
+
+
+def split_noise_generator(step: int, device="cpu", base_seed: int = 0) -> torch.Generator:
+    """Generator for `split_points`' `torch.normal` (avatar/common/nets/module.py:198).  Replicas must clone and split
+    the SAME Gaussians at the SAME offsets or their parameter sets diverge; seeding from the step counter (identical on
+    every rank) instead of the process-global RNG makes the draw independent of what each rank rendered before."""
+    g = torch.Generator(device=device)
+    g.manual_seed((int(base_seed) * 1_000_003 + int(step)) & 0x7FFFFFFF)
+    return g

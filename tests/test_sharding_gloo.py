@@ -12,7 +12,8 @@ import torch.multiprocessing as mp
 
 from exavatar_release_b200.camera import look_at_cam_param
 from exavatar_release_b200.renderer import GaussianRenderer
-from exavatar_release_b200.sharding import GradBucket, shard_frames, sharded_step
+from exavatar_release_b200.sharding import (GradBucket, reduce_densify_stats, shard_frames, sharded_step,
+                                            split_noise_generator)
 from exavatar_release_b200.synthetic import make_assets, make_grad_image
 
 KEYS = ("mean_3d", "scale", "rotation", "opacity", "rgb", "mean_2d")
@@ -80,3 +81,33 @@ def test_two_ranks_equal_single_process():
     mp.spawn(_worker, args=(2, port, yaws, ret), nprocs=2, join=True)
     assert np.array_equal(ret[0], ret[1])  # every rank holds the same reduced bucket
     assert np.allclose(ret[0], ref, rtol=1e-5, atol=1e-6 * np.abs(ref).max())
+
+
+def _stats_worker(rank, world, port, ret):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    g = torch.Generator().manual_seed(100 + rank)  # every rank saw different frames
+    stats = {"grad_accum": torch.rand(50, generator=g), "count": torch.randint(0, 3, (50,), generator=g).float(),
+             "radius_max": torch.randint(0, 30, (50,), generator=g).float()}
+    local = {k: v.clone() for k, v in stats.items()}
+    reduce_densify_stats(stats)
+    noise = torch.normal(torch.zeros(7, 3), torch.ones(7, 3), generator=split_noise_generator(step=1234))
+    ret[rank] = ({k: v.numpy() for k, v in local.items()}, {k: v.numpy() for k, v in stats.items()}, noise.numpy())
+    dist.destroy_process_group()
+
+
+def test_densify_statistics_reduce_sum_sum_max_and_split_noise_is_identical_on_every_rank():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_stats_worker, args=(2, port, ret), nprocs=2, join=True)
+    (l0, r0, n0), (l1, r1, n1) = ret[0], ret[1]
+    assert np.allclose(r0["grad_accum"], l0["grad_accum"] + l1["grad_accum"]) and np.array_equal(r0["grad_accum"], r1["grad_accum"])
+    assert np.array_equal(r0["count"], l0["count"] + l1["count"]) and np.array_equal(r0["count"], r1["count"])
+    assert np.array_equal(r0["radius_max"], np.maximum(l0["radius_max"], l1["radius_max"]))
+    assert np.array_equal(n0, n1)  # same step -> same split offsets on both replicas
+    other = torch.normal(torch.zeros(7, 3), torch.ones(7, 3), generator=split_noise_generator(step=1235)).numpy()
+    assert not np.array_equal(n0, other)
