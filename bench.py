@@ -72,6 +72,7 @@ def parse():
                     help="five pattern: merged = two projection/binning passes shared by the five renders (SURVEY 8f-3); "
                          "separate = five independent renders on five streams (round-1 FiveRenderPlan)")
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
+    ap.add_argument("--no-graph-collectives", action="store_true", help="N > 1: issue the all-reduces after the graph replay")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-eager", action="store_true", help="skip the e2e_eager leg")
     ap.add_argument("--no-single", action="store_true", help="five pattern: skip the extra C2 single-render key")
@@ -425,7 +426,7 @@ def make_five_engine(kind, Ps, Ph, W, H, caps, dev):
 def bench_five(env, args, wl, wl_key):
     from exavatar_release_b200 import rasterizer as RZ
     from exavatar_release_b200.renderer import GaussianRenderer, render_settings
-    from exavatar_release_b200.sharding import reduce_densify_stats, shard_frames
+    from exavatar_release_b200.sharding import shard_frames
     dev, lib, world, rank = env.dev, env.lib, env.world, env.rank
     F, K, Wm = args.frames, args.steps, max(args.warmup, 3)
     H, Wd = wl.height, wl.width
@@ -465,11 +466,11 @@ def bench_five(env, args, wl, wl_key):
         engines.append(e)
     engine = engines[0]
     lane_streams = [torch.cuda.Stream(dev) for _ in range(S)]
-    mk_stats = lambda: {"grad_accum": torch.zeros(Ps, device=dev), "count": torch.zeros(Ps, device=dev),
-                        "radius_max": torch.zeros(Ps, device=dev)}
-    lane_stats = [mk_stats() for _ in range(S)]
-    stats = lane_stats[0]  # SceneGaussian.xyz_grad_accum / track_cnt / radius_max of the step (after the lane fold)
-    flat = engine.flat_bucket()  # ONE flat fp32 buffer: every per-Gaussian gradient of the three parameter sets
+    # densification statistics of the step: the two sums live at the tail of each engine's flat bucket (one sum all-reduce
+    # covers gradients and statistics), the maximum is its own small tensor
+    lane_stats = [dict(e.stats(), radius_max=torch.zeros(Ps, device=dev)) for e in engines]
+    stats = lane_stats[0]  # xyz_grad_accum / track_cnt increments and radius_max of the step (after the lane fold)
+    flat = engine.flat_bucket()  # ONE flat fp32 buffer: every per-Gaussian gradient of the three parameter sets + the sums
 
     def body_for(frame_ids, sts_w, sts_r, scale=None):
         gimgs = g5 if scale is None else [{r: g * scale for r, g in gf.items()} for gf in g5]
@@ -483,6 +484,8 @@ def bench_five(env, args, wl, wl_key):
                 with torch.cuda.stream(st_):
                     e = engines[s_]
                     e.set_scene(scene_a)
+                    e.zero_stats()
+                    lane_stats[s_]["radius_max"].zero_()
                     for j, idx in enumerate(range(s_, len(frame_ids), S)):
                         f = frame_ids[idx]
                         e.frame(("f", f), sts_w[idx], sts_r[idx], scene_a, human_a, refined_a, gimgs[f % 8],
@@ -490,30 +493,49 @@ def bench_five(env, args, wl, wl_key):
                     e.reduce()
             for s_ in range(used):
                 cur.wait_stream(lane_streams[s_])
-            for s_ in range(1, used):  # fold the lanes, fixed order
+            for s_ in range(1, used):  # fold the lanes, fixed order (the statistics sums are part of the bucket)
                 flat.add_(engines[s_].flat_bucket())
-                stats["grad_accum"].add_(lane_stats[s_]["grad_accum"])
-                stats["count"].add_(lane_stats[s_]["count"])
                 torch.maximum(stats["radius_max"], lane_stats[s_]["radius_max"], out=stats["radius_max"])
         return body
 
     body = body_for(weak_frames, st_w, st_r)
     graph, launches_per_step = (None, 0)
+    coll_in_graph = False
     if not args.no_graph:
-        graph, launches_per_step = env.capture(body)
+        if world > 1 and not args.no_graph_collectives:
+            # the collectives as nodes of the step graph: no host launch gap between the last kernel and the all-reduce
+            try:
+                for _ in range(2):  # NCCL warm-up outside the capture
+                    env.dist.all_reduce(flat)
+                    env.dist.all_reduce(lane_stats[0]["radius_max"], op=env.dist.ReduceOp.MAX)
+                torch.cuda.synchronize(dev)
+
+                def body_c():
+                    body()
+                    env.dist.all_reduce(flat)
+                    env.dist.all_reduce(lane_stats[0]["radius_max"], op=env.dist.ReduceOp.MAX)
+                graph, launches_per_step = env.capture(body_c)
+                coll_in_graph = True
+            except Exception as exc:
+                print(f"bench.py: capturing the collectives failed ({type(exc).__name__}: {exc}); issuing them after the replay",
+                      file=sys.stderr)
+                torch.cuda.synchronize(dev)
+                graph = None
+        if graph is None:
+            graph, launches_per_step = env.capture(body)
 
     def collectives():
-        """one gradient all-reduce per step + the small densification-statistics reduction
-        (module.py:111-113,155-157: xyz_grad_accum sum, track_cnt sum, radius_max max)."""
+        """ONE sum all-reduce of the flat bucket (gradients + the xyz_grad_accum / track_cnt increments of
+        module.py:155-157 at its tail) and one small max all-reduce (radius_max, model.py:283-285)."""
         env.dist.all_reduce(flat)
-        reduce_densify_stats(stats)
+        env.dist.all_reduce(stats["radius_max"], op=env.dist.ReduceOp.MAX)
 
     def step():
         if graph is not None:
             graph.replay()
         else:
             body()
-        if world > 1:
+        if world > 1 and not coll_in_graph:
             collectives()
 
     for _ in range(Wm):
@@ -538,8 +560,9 @@ def bench_five(env, args, wl, wl_key):
         for _ in range(3):
             collectives()
         ms_c, _, _ = env.timed(collectives, 10)
-        coll = {"ms_per_step": ms_c / 10, "bucket_bytes": int(flat.numel() * 4),
-                "what": "ncclAllReduce(sum) of the flat gradient bucket + 3 small densification-stat all-reduces (sum, sum, max)"}
+        coll = {"ms_per_step": ms_c / 10, "bucket_bytes": int(flat.numel() * 4), "in_step_graph": coll_in_graph,
+                "what": "ncclAllReduce(sum) of the flat bucket (gradients + densification sums) + one small max all-reduce "
+                        "(radius_max), timed alone"}
 
     # ---- per-kernel durations: the renders of one step, one at a time, in-library events ----
     lib.b2r_profile_enable(1)

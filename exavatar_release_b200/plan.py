@@ -213,13 +213,17 @@ class FiveRenderPlan:
         # one allocation: [scene | human | human_refined | scene_human | scene_human_refined]; the first three segments
         # are what reduce() leaves the step's gradients in
         order = ("scene", "human", "human_refined", "scene_human", "scene_human_refined")
-        self.all_flat = torch.zeros(self.PER * sum(out_rows[r] for r in order), dtype=torch.float32, device=device)
+        tail = 2 * self.Ps  # per-step densification sums of the scene Gaussians ride in the all-reduced buffer (stats())
+        self.all_flat = torch.zeros(self.PER * sum(out_rows[r] for r in order) + tail, dtype=torch.float32, device=device)
         self.flat, self.views, o = {}, {}, 0
         for r in order:
             n = self.PER * out_rows[r]
             self.flat[r], self.views[r] = _views_of(self.all_flat[o:o + n], out_rows[r])
             o += n
-        self._reduced = self.PER * (self.Ps + 2 * self.Ph)
+            if r == "human_refined":
+                self._stats = self.all_flat[o:o + tail]
+                o += tail
+        self._reduced = self.PER * (self.Ps + 2 * self.Ph) + tail
         f = lambda w: torch.empty(self.Ps + self.Ph, w, dtype=torch.float32, device=device)
         widths = {"mean_3d": 3, "opacity": 1, "scale": 3, "rotation": 4, "rgb": 3}
         self.cat = {r: {k: f(w) for k, w in widths.items()} for r in ("scene_human", "scene_human_refined")}
@@ -283,6 +287,14 @@ class FiveRenderPlan:
 
     def flat_bucket(self) -> torch.Tensor:
         return self.all_flat[: self._reduced]
+
+    def stats(self) -> Dict[str, torch.Tensor]:
+        """Per-step sums of ExAvatar's densification statistics (module.py:155-157), stored at the tail of the flat
+        bucket so the step's ONE sum all-reduce covers them; zero them at the start of a step (`zero_stats`)."""
+        return {"grad_accum": self._stats[: self.Ps], "count": self._stats[self.Ps:]}
+
+    def zero_stats(self) -> None:
+        self._stats.zero_()
 
     def dups(self) -> Dict[str, int]:
         return {r: p.status()["num_dups"] for r, p in self.plans.items()}
@@ -358,7 +370,8 @@ class MergedFivePlan:
         self.pass_streams = {k: torch.cuda.Stream(self.device) for k in self.passes}
         # one flat gradient buffer: [pass A: scene rows | human rows][pass B: refined rows]
         nA, nB = self.PER * self.P, self.PER * self.Ph
-        self.all_flat = torch.zeros(nA + nB, dtype=torch.float32, device=device)
+        self.all_flat = torch.zeros(nA + nB + 2 * self.Ps, dtype=torch.float32, device=device)
+        self._stats = self.all_flat[nA + nB:]  # per-step densification sums ride in the all-reduced buffer (stats())
         _, self.views_A = _views_of(self.all_flat[:nA], self.P)
         _, self.views_B = _views_of(self.all_flat[nA:], self.Ph)
         Ps, P = self.Ps, self.P
@@ -595,6 +608,13 @@ class MergedFivePlan:
 
     def flat_bucket(self) -> torch.Tensor:
         return self.all_flat
+
+    def stats(self) -> Dict[str, torch.Tensor]:
+        """Per-step sums of the densification statistics at the tail of the flat bucket (see FiveRenderPlan.stats)."""
+        return {"grad_accum": self._stats[: self.Ps], "count": self._stats[self.Ps:]}
+
+    def zero_stats(self) -> None:
+        self._stats.zero_()
 
     def dups(self) -> Dict[str, int]:
         return {k: ps.status()["num_dups"] for k, ps in self.passes.items()}
