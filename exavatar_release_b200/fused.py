@@ -23,6 +23,13 @@ the reference), likewise for the refined set.  INTEGRATION.md shows the replacem
 The duplicate capacity is fixed per instance (every buffer is resident; nothing is polled or synchronised, so the call
 is capturable in a CUDA graph); `overflowed()` reports if a frame needed more (its lists were truncated, never corrupt).
 One frame may be in flight per instance: run backward (or drop the outputs) before the next call.
+
+`use_graph=True`: the first frame captures the forward and the backward of the plan into two CUDA graphs; later frames
+copy their inputs into the plan's resident buffers (assets, camera, dL/dimage) and replay.  The Python cost of a frame
+drops from ~2.9 ms (hundreds of stream switches, ctypes calls and small copies) to a few copies and two graph launches,
+so an otherwise EAGER training loop runs the raster part at graph speed.  Kernel arguments passed by value are frozen in
+the graphs, so a change of the intrinsics (tan fov) re-captures; every render's backward runs (a render left out of the
+loss contributes zeros).
 """
 from __future__ import annotations
 
@@ -45,9 +52,12 @@ class _FrameFn(torch.autograd.Function):
         plan: MergedFivePlan = mod.plan
         scene, human, refined = (dict(zip(_KEYS, (_f32c(t.detach(), k) for k, t in zip(_KEYS, tensors[i * 5:i * 5 + 5]))))
                                  for i in range(3))
-        plan.set_scene(scene)
         mod._frame_no += 1
-        plan.forward_frame(None, settings, settings_h, scene, human, refined)  # no descriptor cache: cameras change
+        if mod.use_graph:
+            mod._graph_forward(settings, settings_h, scene, human, refined)
+        else:
+            plan.set_scene(scene)
+            plan.forward_frame(None, settings, settings_h, scene, human, refined)  # no descriptor cache: cameras change
         outs = []
         for r in RENDERS:  # fresh tensors: the plan's image buffers are overwritten by the next frame
             pk = "A" if r in plan.VIEWS["A"] else "B"
@@ -70,11 +80,15 @@ class _FrameFn(torch.autograd.Function):
         gd = {r: (None if g[3 * i + 1] is None else _f32c(g[3 * i + 1], "grad_depth")) for i, r in enumerate(RENDERS)}
         ga = {r: (None if g[3 * i + 2] is None else _f32c(g[3 * i + 2], "grad_alpha")) for i, r in enumerate(RENDERS)}
         dev = plan.device
-        flat_a = torch.empty(plan.PER * plan.P, dtype=torch.float32, device=dev)
-        flat_b = torch.empty(plan.PER * plan.Ph, dtype=torch.float32, device=dev)
+        if mod.use_graph:
+            flat_a, flat_b = mod._graph_backward(gc, gd, ga)  # fresh copies of the resident gradient buffers
+        else:
+            flat_a = torch.empty(plan.PER * plan.P, dtype=torch.float32, device=dev)
+            flat_b = torch.empty(plan.PER * plan.Ph, dtype=torch.float32, device=dev)
         _, va = _views_of(flat_a, plan.P)
         _, vb = _views_of(flat_b, plan.Ph)
-        plan.backward_frame(gc, va, vb, g_depths=gd, g_alphas=ga, densify=mod.densify)
+        if not mod.use_graph:
+            plan.backward_frame(gc, va, vb, g_depths=gd, g_alphas=ga, densify=mod.densify)
         Ps = plan.Ps
         out = [None, None, None, va["means2D"][:Ps].reshape(ctx.m2d_shape)]
         for part in (lambda v: v[:Ps], lambda v: v[Ps:]):
@@ -88,12 +102,101 @@ class _FrameFn(torch.autograd.Function):
 
 
 class TrainingFrameRenderer(nn.Module):
-    def __init__(self, P_scene: int, P_human: int, img_shape, device, dup_capacity: Optional[Dict[str, int]] = None):
+    def __init__(self, P_scene: int, P_human: int, img_shape, device, dup_capacity: Optional[Dict[str, int]] = None,
+                 use_graph: bool = False, graph_depth_alpha: bool = False):
         super().__init__()
         self.img_shape = (int(img_shape[0]), int(img_shape[1]))
         self.plan = MergedFivePlan(P_scene, P_human, self.img_shape[1], self.img_shape[0], dup_capacity, device)
         self.densify = None  # optional {'grad_accum','count','radius_max'} (P_scene) tensors updated by the backward
         self._frame_no = 0
+        self.use_graph = bool(use_graph)
+        if self.use_graph:
+            dev, (H, W), plan = self.plan.device, self.img_shape, self.plan
+            # resident camera / background block the captured kernels read: view (16) | full projection (16) | campos (3) |
+            # bg (3) | bg of the human-only renders (3)
+            self._cam = torch.zeros(41, dtype=torch.float32, device=dev)
+            self._gin = {r: torch.zeros(3, H, W, dtype=torch.float32, device=dev) for r in RENDERS}
+            # dL/ddepth and dL/dalpha inputs only when asked for: their backward variant is the slower one
+            self._gin_d = {r: torch.zeros(1, H, W, dtype=torch.float32, device=dev) for r in RENDERS} if graph_depth_alpha else None
+            self._gin_a = {r: torch.zeros(1, H, W, dtype=torch.float32, device=dev) for r in RENDERS} if graph_depth_alpha else None
+            self._flat_a = torch.zeros(plan.PER * plan.P, dtype=torch.float32, device=dev)
+            self._flat_b = torch.zeros(plan.PER * plan.Ph, dtype=torch.float32, device=dev)
+            self._graphs = {}  # (tanfovx, tanfovy) -> (settings, settings_h, forward graph, backward graph)
+            self._cur = None
+
+    # ---- use_graph=True ----
+    def _resident_settings(self, settings, settings_h):
+        c = self._cam
+        mk = lambda bg: GaussianRasterizationSettings(
+            image_height=settings.image_height, image_width=settings.image_width, tanfovx=settings.tanfovx,
+            tanfovy=settings.tanfovy, bg=bg, scale_modifier=settings.scale_modifier, viewmatrix=c[0:16].view(4, 4),
+            projmatrix=c[16:32].view(4, 4), sh_degree=0, campos=c[32:35], prefiltered=False, debug=False)
+        return mk(c[35:38]), mk(c[38:41])
+
+    def _load_inputs(self, settings, settings_h, scene, human, refined):
+        plan, c = self.plan, self._cam
+        c[0:16].copy_(settings.viewmatrix.reshape(16))
+        c[16:32].copy_(settings.projmatrix.reshape(16))
+        c[32:35].copy_(settings.campos.reshape(3))
+        c[35:38].copy_(settings.bg.reshape(3))
+        c[38:41].copy_(settings_h.bg.reshape(3))
+        pa, pb = plan.passes["A"], plan.passes["B"]
+        for k in _KEYS:
+            pa.cat[k][: plan.Ps].copy_(scene[k].reshape(plan.Ps, -1))
+            pa.cat[k][plan.Ps:].copy_(human[k].reshape(plan.Ph, -1))
+            pb.cat[k][plan.Ps:].copy_(refined[k].reshape(plan.Ph, -1))
+
+    def _graph_forward(self, settings, settings_h, scene, human, refined):
+        plan = self.plan
+        self._load_inputs(settings, settings_h, scene, human, refined)
+        dn = self.densify or {}
+        key = (float(settings.tanfovx), float(settings.tanfovy), float(settings.scale_modifier),
+               tuple(0 if dn.get(k) is None else dn[k].data_ptr() for k in ("grad_accum", "count", "radius_max")))
+        if key not in self._graphs:
+            st, st_h = self._resident_settings(settings, settings_h)
+            pa, pb = plan.passes["A"], plan.passes["B"]
+            _, va = _views_of(self._flat_a, plan.P)
+            _, vb = _views_of(self._flat_b, plan.Ph)
+
+            def fwd():
+                for k in _KEYS:  # the scene rows of pass B come from pass A's copy
+                    pb.cat[k][: plan.Ps].copy_(pa.cat[k][: plan.Ps])
+                plan.forward_frame(("graph", key), st, st_h, None, None, None, copy_inputs=False)
+
+            def bwd():
+                plan.backward_frame(self._gin, va, vb, g_depths=self._gin_d, g_alphas=self._gin_a, densify=self.densify)
+
+            cur = torch.cuda.current_stream(plan.device)
+            side = torch.cuda.Stream(plan.device)
+            side.wait_stream(cur)
+            with torch.cuda.stream(side):  # warm-up (also primes the ctx counters), then capture
+                fwd()
+                bwd()
+            cur.wait_stream(side)
+            torch.cuda.synchronize(plan.device)
+            gf, gb = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+            with torch.cuda.graph(gf):
+                fwd()
+            with torch.cuda.graph(gb, pool=gf.pool()):
+                bwd()
+            self._graphs[key] = (st, st_h, gf, gb)
+        self._cur = self._graphs[key]
+        self._cur[2].replay()
+
+    def _graph_backward(self, gc, gd, ga):
+        for dst, src in ((self._gin, gc), (self._gin_d, gd), (self._gin_a, ga)):
+            if dst is None:
+                if any(v is not None for v in src.values()):
+                    raise RuntimeError("TrainingFrameRenderer(use_graph=True): gradients of depthmap / mask need "
+                                       "graph_depth_alpha=True")
+                continue
+            for r in RENDERS:
+                if src[r] is None:
+                    dst[r].zero_()
+                else:
+                    dst[r].copy_(src[r].reshape(dst[r].shape))
+        self._cur[3].replay()
+        return self._flat_a.clone(), self._flat_b.clone()
 
     def overflowed(self) -> bool:
         return self.plan.overflowed()

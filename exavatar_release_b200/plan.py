@@ -489,9 +489,10 @@ class MergedFivePlan:
                 cur.wait_stream(self.pass_streams[pk])
 
     # ---- the same frame in two halves (forward now, backward when the caller's gradients exist): fused.py ----
-    def forward_frame(self, key, settings, settings_human_bg, scene, human, refined) -> None:
+    def forward_frame(self, key, settings, settings_human_bg, scene, human, refined, copy_inputs: bool = True) -> None:
         """Forward of the five renders; images in `render_outputs()`, per-pixel state and checkpoints stay in the plan
-        until `backward_frame` (so the plan must not start another frame in between)."""
+        until `backward_frame` (so the plan must not start another frame in between).  copy_inputs=False: the caller
+        already wrote the human / refined rows into `passes[*].cat` (a captured graph keeps the copies outside)."""
         lib = self.lib
         cur = torch.cuda.current_stream(self.device)
         bg_h = _f32c(settings_human_bg.bg.to(self.device), "bg")
@@ -505,9 +506,10 @@ class MergedFivePlan:
             st = self.pass_streams[pk]
             st.wait_stream(cur)
             with torch.cuda.stream(st):
-                src = human if pk == "A" else refined
-                for k, buf in ps.cat.items():
-                    buf[self.Ps:].copy_(src[k].reshape(self.Ph, -1))
+                if copy_inputs:
+                    src = human if pk == "A" else refined
+                    for k, buf in ps.cat.items():
+                        buf[self.Ps:].copy_(src[k].reshape(self.Ph, -1))
                 sc = self._scene_desc((key, pk), ps, settings)
                 sc.flags = L.B2R_FLAG_CTX_CLEAN if ps.primed else 0
                 ps.primed = True

@@ -594,11 +594,13 @@ def test_five_render_plan_matches_the_reference_pattern(dev, engine):
     assert float(lv["scene"]["mean_3d"].grad.abs().sum()) > 0 and float(lv["refined"]["rgb"].grad.abs().sum()) > 0
 
 
-def test_training_frame_renderer_equals_five_renderer_calls(dev):
+@pytest.mark.parametrize("use_graph", [False, True])
+def test_training_frame_renderer_equals_five_renderer_calls(dev, use_graph):
     """`TrainingFrameRenderer` (one autograd call, two merged passes) against the reference's five `GaussianRenderer`
     calls written with the drop-in rasteriser (avatar/main/model.py:117-162): images, masks, radii, and the gradients
     `loss.backward()` leaves in the three asset dicts and in the scene render's mean_2d; a render left out of the loss
-    gets no backward launch."""
+    gets no backward launch (eager) or a zero dL/dimage (use_graph: the frame replays two captured CUDA graphs, three
+    frames so that the third is a pure replay with a new camera)."""
     from exavatar_release_b200 import GaussianRenderer, TrainingFrameRenderer
     from exavatar_release_b200.camera import look_at_cam_param
     from exavatar_release_b200.plan import RENDERS
@@ -613,8 +615,9 @@ def test_training_frame_renderer_equals_five_renderer_calls(dev):
     used = ("scene", "human", "scene_human", "scene_human_refined")  # human_refined stays out of the loss
     mk = lambda: {n: {k: v.clone().requires_grad_() for k, v in a.items()} for n, a in
                   (("scene", scene), ("human", human), ("refined", refined))}
-    frame = TrainingFrameRenderer(Ps, Ph, (H, W), dev, {"A": 2_000_000, "B": 2_000_000})
-    for yaw in (-9.0, 6.0):  # two frames through the same instance
+    frame = TrainingFrameRenderer(Ps, Ph, (H, W), dev, {"A": 2_000_000, "B": 2_000_000}, use_graph=use_graph,
+                                  graph_depth_alpha=use_graph)
+    for yaw in (-9.0, 6.0, 14.0):  # three frames through the same instance
         cam = look_at_cam_param(yaw, (H, W), device=dev)
         a = mk()
         R = GaussianRenderer()
