@@ -26,7 +26,10 @@ NVCC_FLAGS = [
 # expression order (SURVEY.md section 7.2 "bit-compatible discrete decisions"), so radii / rects / centres are identical
 # bit for bit instead of "equal except when 3 sqrt(lambda) lands within an ulp of an integer".  The kernel is
 # latency-bound; the ~100 extra FP instructions per Gaussian do not show in its duration.
-PER_FILE_FLAGS = {"project.cu": ["--fmad=false"]}
+# binning.cu: its scatter repeats the projection's tile region test for rects of more than 32 tiles (smaller ones replay
+# a stored mask); the two must agree on every (splat, tile) pair or a list slot stays unfilled, so the unit is compiled
+# with the same contraction setting (its kernels are integer sorts otherwise).
+PER_FILE_FLAGS = {"project.cu": ["--fmad=false"], "binning.cu": ["--fmad=false"]}
 
 
 def sources():

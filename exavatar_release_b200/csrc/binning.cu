@@ -18,72 +18,32 @@ __global__ void __launch_bounds__(256) scatter_kernel(const B2RScene sc, const C
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int4 aux = make_int4(0, 0, 0, 0);
   float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+  uint32_t depth_bits = 0u;
   if (i < sc.P) {
     aux = cx.aux[i];
     if (aux.z > 0) {
-      g0 = reinterpret_cast<const float4*>(cx.geom + i)[0];
-      g1 = reinterpret_cast<const float4*>(cx.geom + i)[1];
+      const int area = ((aux.y & 0xffff) - (aux.x & 0xffff)) * ((aux.y >> 16) - (aux.x >> 16));
+      depth_bits = __float_as_uint(cx.geom[i].g1.z);
+      if (area > 32) {  // only these repeat the region test (warp_replay_kept_tiles)
+        g0 = reinterpret_cast<const float4*>(cx.geom + i)[0];
+        g1 = reinterpret_cast<const float4*>(cx.geom + i)[1];
+      }
     }
   }
   const uint64_t cap = cx.dup_capacity;
   const int gx = cx.gx;
   uint32_t* cursor = cx.tile_cursor;
   uint2* keys = cx.keys;
-  const bool no_cull = (sc.flags & B2R_FLAG_NO_TILE_CULL) != 0;
-  const int W = sc.width, H = sc.height;
-  // Same enumeration and the same predicate as the counting pass in project_kernel (warp_for_each_kept_tile), but
-  // written out so that the slot-claiming atomics (ATOMG with a ~700-cycle round trip; 2/3 of this kernel's stall
-  // samples in the first profile) overlap: a lane issues all atomics of a small rect before its first store, and the
-  // cooperative walk of a large rect stores its slots one Gaussian late.
-  auto keep_tile = [&](int tx, int ty, float sx, float sy, float a2, float b2, float c2, float th) {
-    if (no_cull) return true;
-    const float rx0 = (float)(tx * TILE), ry0 = (float)(ty * TILE);
-    const float rx1 = fminf(rx0 + (float)(TILE - 1), (float)(W - 1));
-    const float ry1 = fminf(ry0 + (float)(TILE - 1), (float)(H - 1));
-    return !(region_max_p2(sx, sy, a2, b2, c2, rx0, ry0, rx1, ry1) < th);
-  };
-  const int lane = threadIdx.x & 31;
-  const bool active = aux.z > 0;
-  const int x0 = aux.x & 0xffff, y0 = aux.x >> 16, x1 = aux.y & 0xffff, y1 = aux.y >> 16;
-  const int w = x1 - x0;
-  const int area = active ? w * (y1 - y0) : 0;
-  const uint32_t depth_bits = __float_as_uint(g1.z);
-  constexpr int SMALL = 4;  // must equal warp_for_each_kept_tile's threshold (same pairs either way)
+  // The slot-claiming atomics (ATOMG with a ~700-cycle round trip; 2/3 of this kernel's stall samples in the first
+  // profile) overlap: a pair is stored one claim late, when its slot number has had time to come back.
   constexpr uint32_t NONE = 0xffffffffu;
-  if (area > 0 && area <= SMALL) {
-    uint32_t pos[SMALL];
-#pragma unroll
-    for (int t = 0; t < SMALL; t++) {
-      pos[t] = NONE;
-      if (t < area) {
-        const int ty = y0 + t / w, tx = x0 + t - (t / w) * w;
-        if (keep_tile(tx, ty, g0.x, g0.y, g0.z, g0.w, g1.x, g1.w)) pos[t] = atomicAdd(cursor + ty * gx + tx, 1u);
-      }
-    }
-#pragma unroll
-    for (int t = 0; t < SMALL; t++)
-      if (pos[t] < cap) keys[pos[t]] = make_uint2(depth_bits, (uint32_t)i);  // NONE >= cap always
-  }
-  unsigned mask = __ballot_sync(0xffffffffu, area > SMALL);
   uint32_t pend_pos = NONE, pend_depth = 0, pend_id = 0;
-  while (mask) {
-    const int src = __ffs(mask) - 1;
-    mask &= mask - 1;
-    const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
-    const int bw = __shfl_sync(0xffffffffu, w, src), barea = __shfl_sync(0xffffffffu, area, src);
-    const float spx = __shfl_sync(0xffffffffu, g0.x, src), spy = __shfl_sync(0xffffffffu, g0.y, src);
-    const float sA = __shfl_sync(0xffffffffu, g0.z, src), sB = __shfl_sync(0xffffffffu, g0.w, src);
-    const float sC = __shfl_sync(0xffffffffu, g1.x, src), sT = __shfl_sync(0xffffffffu, g1.w, src);
-    const uint32_t sd = __shfl_sync(0xffffffffu, depth_bits, src), sid = __shfl_sync(0xffffffffu, (uint32_t)i, src);
-    for (int t = lane; t < barea; t += 32) {
-      const int r = t / bw;
-      const int ty = by0 + r, tx = bx0 + t - r * bw;
-      uint32_t p = NONE;
-      if (keep_tile(tx, ty, spx, spy, sA, sB, sC, sT)) p = atomicAdd(cursor + ty * gx + tx, 1u);
-      if (pend_pos < cap) keys[pend_pos] = make_uint2(pend_depth, pend_id);  // the previous claim has landed by now
-      pend_pos = p; pend_depth = sd; pend_id = sid;
-    }
-  }
+  warp_replay_kept_tiles(aux.z > 0, aux.x & 0xffff, aux.x >> 16, aux.y & 0xffff, aux.y >> 16, (uint32_t)aux.w, g0.x, g0.y,
+                         g0.z, g0.w, g1.x, g1.w, depth_bits, (uint32_t)i, (sc.flags & B2R_FLAG_NO_TILE_CULL) != 0, sc.width,
+                         sc.height, gx, cursor, [&](uint32_t p, int, uint32_t d, uint32_t id) {
+                           if (pend_pos < cap) keys[pend_pos] = make_uint2(pend_depth, pend_id);  // NONE >= cap always
+                           pend_pos = p; pend_depth = d; pend_id = id;
+                         });
   if (pend_pos < cap) keys[pend_pos] = make_uint2(pend_depth, pend_id);
 }
 
@@ -91,7 +51,7 @@ __global__ void __launch_bounds__(256) scatter_kernel(const B2RScene sc, const C
 // the same global address serialise in L2 (~15 ns each on the hot avatar tiles, which receive thousands), so a CTA
 // claims its slots of a tile with ONE global atomic: (1) count the CTA's pairs per tile in shared memory, (2) one
 // atomicAdd per touched tile reserves a contiguous run of the tile's segment, (3) enumerate again and drop each pair
-// at run base + its rank inside the CTA (shared-memory atomic).  The region test runs twice; it is ~40 instructions.
+// at run base + its rank inside the CTA (shared-memory atomic).  Both enumerations replay the projection's kept masks.
 __global__ void __launch_bounds__(256) scatter_agg_kernel(const B2RScene sc, const Ctx cx) {
   extern __shared__ uint32_t s_mem[];
   uint32_t* s_cnt = s_mem;              // [tiles] pairs of this CTA per tile, then the running rank
@@ -101,18 +61,24 @@ __global__ void __launch_bounds__(256) scatter_agg_kernel(const B2RScene sc, con
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   int4 aux = make_int4(0, 0, 0, 0);
   float4 g0 = make_float4(0.f, 0.f, 0.f, 0.f), g1 = g0;
+  uint32_t depth_bits = 0u;
   if (i < sc.P) {
     aux = cx.aux[i];
     if (aux.z > 0) {
-      g0 = reinterpret_cast<const float4*>(cx.geom + i)[0];
-      g1 = reinterpret_cast<const float4*>(cx.geom + i)[1];
+      const int area = ((aux.y & 0xffff) - (aux.x & 0xffff)) * ((aux.y >> 16) - (aux.x >> 16));
+      depth_bits = __float_as_uint(cx.geom[i].g1.z);
+      if (area > 32) {  // only these repeat the region test (warp_replay_kept_tiles)
+        g0 = reinterpret_cast<const float4*>(cx.geom + i)[0];
+        g1 = reinterpret_cast<const float4*>(cx.geom + i)[1];
+      }
     }
   }
   const int gx = cx.gx;
   const bool no_cull = (sc.flags & B2R_FLAG_NO_TILE_CULL) != 0;
   const int x0 = aux.x & 0xffff, y0 = aux.x >> 16, x1 = aux.y & 0xffff, y1 = aux.y >> 16;
-  warp_for_each_kept_tile(aux.z > 0, x0, y0, x1, y1, g0.x, g0.y, g0.z, g0.w, g1.x, g1.w, 0u, 0u, no_cull, sc.width,
-                          sc.height, [&](int tx, int ty, uint32_t, uint32_t) { atomicAdd(&s_cnt[ty * gx + tx], 1u); });
+  const uint32_t kept = (uint32_t)aux.w;
+  warp_replay_kept_tiles(aux.z > 0, x0, y0, x1, y1, kept, g0.x, g0.y, g0.z, g0.w, g1.x, g1.w, 0u, 0u, no_cull, sc.width,
+                         sc.height, gx, s_cnt, [](uint32_t, int, uint32_t, uint32_t) {});
   __syncthreads();
   for (int t = threadIdx.x; t < cx.tiles; t += blockDim.x) {
     const uint32_t c = s_cnt[t];
@@ -124,12 +90,11 @@ __global__ void __launch_bounds__(256) scatter_agg_kernel(const B2RScene sc, con
   __syncthreads();
   const uint64_t cap = cx.dup_capacity;
   uint2* keys = cx.keys;
-  warp_for_each_kept_tile(aux.z > 0, x0, y0, x1, y1, g0.x, g0.y, g0.z, g0.w, g1.x, g1.w, __float_as_uint(g1.z), (uint32_t)i,
-                          no_cull, sc.width, sc.height, [&](int tx, int ty, uint32_t depth_bits, uint32_t id) {
-                            const int t = ty * gx + tx;
-                            const uint32_t pos = s_base[t] + atomicAdd(&s_cnt[t], 1u);
-                            if (pos < cap) keys[pos] = make_uint2(depth_bits, id);
-                          });
+  warp_replay_kept_tiles(aux.z > 0, x0, y0, x1, y1, kept, g0.x, g0.y, g0.z, g0.w, g1.x, g1.w, depth_bits, (uint32_t)i,
+                         no_cull, sc.width, sc.height, gx, s_cnt, [&](uint32_t rank, int t, uint32_t d, uint32_t id) {
+                           const uint32_t pos = s_base[t] + rank;
+                           if (pos < cap) keys[pos] = make_uint2(d, id);
+                         });
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -173,6 +138,8 @@ template <int CAP, int THREADS, bool PAIRS = false>
 __device__ __forceinline__ void radix_sort_tile(const uint2* src, uint32_t* dst, const int n, unsigned char* smem_raw,
                                                 uint32_t* maxid) {
   constexpr int W = THREADS / 32;
+  constexpr int ROWS = CAP / (W * 32);  // 32-key rows of a warp's share of a full chunk
+  static_assert(CAP % (W * 32) == 0, "a warp's share must be whole rows");
   uint32_t* keyA = reinterpret_cast<uint32_t*>(smem_raw);
   uint32_t* keyB = keyA + CAP;
   uint16_t* idxA = reinterpret_cast<uint16_t*>(keyB + CAP);
@@ -207,14 +174,22 @@ __device__ __forceinline__ void radix_sort_tile(const uint2* src, uint32_t* dst,
     for (int i = tid; i < W * 256; i += THREADS) hist[i] = 0;
     __syncthreads();
     uint16_t* myhist = hist + warp * 256;
-    // pass 1: warp-private digit histogram
-    for (int base = c_begin; base < c_end; base += 32) {
-      const int i = base + lane;
-      const bool valid = i < c_end;
-      const uint32_t d = valid ? ((kin[i] >> shift) & 0xffu) : (256u + lane);
-      const unsigned peers = match_digit(d, valid);
-      if (valid && (peers & ((1u << lane) - 1u)) == 0u) myhist[d] = (uint16_t)(myhist[d] + __popc(peers));
-      __syncwarp();
+    // pass 1: warp-private digit histogram; the peer masks (lanes of the row with the same digit) are kept in registers
+    // for the scatter below, which sees the same rows -- the nine ballots of match_digit are a third of a pass
+    unsigned row_peers[ROWS];
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+      const int base = c_begin + 32 * r;
+      row_peers[r] = 0u;
+      if (base < c_end) {  // warp-uniform
+        const int i = base + lane;
+        const bool valid = i < c_end;
+        const uint32_t d = valid ? ((kin[i] >> shift) & 0xffu) : (256u + lane);
+        const unsigned peers = match_digit(d, valid);
+        row_peers[r] = peers;
+        if (valid && (peers & ((1u << lane) - 1u)) == 0u) myhist[d] = (uint16_t)(myhist[d] + __popc(peers));
+        __syncwarp();
+      }
     }
     __syncthreads();
     // scan: hist[w][d] <- first output slot of (digit d, warp w)
@@ -257,25 +232,29 @@ __device__ __forceinline__ void radix_sort_tile(const uint2* src, uint32_t* dst,
     }
     __syncthreads();
     // pass 2: stable scatter
-    for (int base = c_begin; base < c_end; base += 32) {
-      const int i = base + lane;
-      const bool valid = i < c_end;
-      const uint32_t k = valid ? kin[i] : 0u;
-      const uint32_t d = valid ? ((k >> shift) & 0xffu) : (256u + lane);
-      const unsigned peers = match_digit(d, valid);
-      const unsigned below = peers & ((1u << lane) - 1u);
-      uint32_t start = 0;
-      if (valid && below == 0u) {
-        start = myhist[d];
-        myhist[d] = (uint16_t)(start + __popc(peers));
+#pragma unroll
+    for (int r = 0; r < ROWS; r++) {
+      const int base = c_begin + 32 * r;
+      if (base < c_end) {  // warp-uniform
+        const int i = base + lane;
+        const bool valid = i < c_end;
+        const uint32_t k = valid ? kin[i] : 0u;
+        const uint32_t d = (k >> shift) & 0xffu;
+        const unsigned peers = row_peers[r];
+        const unsigned below = peers & ((1u << lane) - 1u);
+        uint32_t start = 0;
+        if (valid && below == 0u) {
+          start = myhist[d];
+          myhist[d] = (uint16_t)(start + __popc(peers));
+        }
+        start = __shfl_sync(0xffffffffu, start, valid ? __ffs(peers) - 1 : lane);
+        if (valid) {
+          const uint32_t o = start + __popc(below);
+          kout[o] = k;
+          iout[o] = iin[i];
+        }
+        __syncwarp();
       }
-      start = __shfl_sync(0xffffffffu, start, __ffs(peers) - 1);
-      if (valid) {
-        const uint32_t o = start + __popc(below);
-        kout[o] = k;
-        iout[o] = iin[i];
-      }
-      __syncwarp();
     }
     __syncthreads();
     { uint32_t* t = kin; kin = kout; kout = t; }
@@ -365,7 +344,23 @@ __device__ __forceinline__ void warp_sort_tile(const uint2* __restrict__ src, ui
     if (((differ >> shift) & 0xffu) == 0u) continue;  // warp-uniform: the whole tile agrees on this digit
     reinterpret_cast<uint4*>(hist)[lane] = make_uint4(0u, 0u, 0u, 0u);  // 32 lanes x 16 bytes = 256 x u16
     __syncwarp();
-    for (int base = 0; base < n; base += 32) {
+    constexpr int CACHED = 8;  // rows whose peer masks stay in registers (see radix_sort_tile): lists up to 256 entries
+    unsigned row_peers[CACHED];
+#pragma unroll
+    for (int r = 0; r < CACHED; r++) {
+      const int base = 32 * r;
+      row_peers[r] = 0u;
+      if (base < n) {
+        const int i = base + lane;
+        const bool valid = i < n;
+        const uint32_t d = valid ? ((kin[i] >> shift) & 0xffu) : (256u + lane);
+        const unsigned peers = match_digit(d, valid);
+        row_peers[r] = peers;
+        if (valid && (peers & below_mask) == 0u) hist[d] = (uint16_t)(hist[d] + __popc(peers));
+        __syncwarp();
+      }
+    }
+    for (int base = 32 * CACHED; base < n; base += 32) {
       const int i = base + lane;
       const bool valid = i < n;
       const uint32_t d = valid ? ((kin[i] >> shift) & 0xffu) : (256u + lane);
@@ -387,26 +382,30 @@ __device__ __forceinline__ void warp_sort_tile(const uint2* __restrict__ src, ui
 #pragma unroll
     for (int r = 0; r < 8; r++) { hist[8 * lane + r] = (uint16_t)run; run += c[r]; }
     __syncwarp();
-    for (int base = 0; base < n; base += 32) {  // stable scatter
-      const int i = base + lane;
-      const bool valid = i < n;
-      const uint32_t k = valid ? kin[i] : 0u;
-      const uint32_t d = valid ? ((k >> shift) & 0xffu) : (256u + lane);
-      const unsigned peers = match_digit(d, valid);
-      const unsigned below = peers & below_mask;
-      uint32_t start = 0;
-      if (valid && below == 0u) {
-        start = hist[d];
-        hist[d] = (uint16_t)(start + __popc(peers));
-      }
-      start = __shfl_sync(0xffffffffu, start, __ffs(peers) - 1);
-      if (valid) {
-        const uint32_t o = start + __popc(below);
-        kout[o] = k;
-        iout[o] = iin[i];
-      }
-      __syncwarp();
-    }
+    auto place_row = [&](const int base, const bool cached, const unsigned cached_peers) {  // stable scatter of one row
+        const int i = base + lane;
+        const bool valid = i < n;
+        const uint32_t k = valid ? kin[i] : 0u;
+        const uint32_t d = valid ? ((k >> shift) & 0xffu) : (256u + lane);
+        const unsigned peers = cached ? cached_peers : match_digit(d, valid);
+        const unsigned below = peers & below_mask;
+        uint32_t start = 0;
+        if (valid && below == 0u) {
+          start = hist[d];
+          hist[d] = (uint16_t)(start + __popc(peers));
+        }
+        start = __shfl_sync(0xffffffffu, start, valid ? __ffs(peers) - 1 : lane);
+        if (valid) {
+          const uint32_t o = start + __popc(below);
+          kout[o] = k;
+          iout[o] = iin[i];
+        }
+        __syncwarp();
+    };
+#pragma unroll
+    for (int r = 0; r < CACHED; r++)
+      if (32 * r < n) place_row(32 * r, true, row_peers[r]);
+    for (int base = 32 * CACHED; base < n; base += 32) place_row(base, false, 0u);
     { uint32_t* t = kin; kin = kout; kout = t; }
     { uint16_t* t = iin; iin = iout; iout = t; }
   }

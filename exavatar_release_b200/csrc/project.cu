@@ -164,7 +164,7 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
           g.g0 = make_float4(px, py, A2, B2);
           g.g1 = make_float4(C2, o, pv.z, thr2);
           g.g2 = make_float4(rgb[0], rgb[1], rgb[2], __uint_as_float((bits << 29) | (uint32_t)i));  // id rides with the record
-          aux = make_int4(x0 | (y0 << 16), x1 | (y1 << 16), radius, (x1 - x0) * (y1 - y0));
+          aux = make_int4(x0 | (y0 << 16), x1 | (y1 << 16), radius, 0);
         }
       }
     }
@@ -173,15 +173,16 @@ __global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const C
     gp[0] = g.g0;
     gp[1] = g.g1;
     gp[2] = g.g2;
-    cx.aux[i] = aux;
   }
-  // per-tile histogram of kept (splat, tile) pairs -- warp-cooperative, exact culling unless disabled
+  // per-tile histogram of kept (splat, tile) pairs -- warp-cooperative, exact culling unless disabled; the kept mask of a
+  // rect of <= 32 tiles rides in aux.w for the scatter
   {
     const int gx = cx.gx;
     uint32_t* tile_count = aggregate ? s_cnt : cx.tile_count;
-    warp_for_each_kept_tile(visible, aux.x & 0xffff, aux.x >> 16, aux.y & 0xffff, aux.y >> 16, g.g0.x, g.g0.y, g.g0.z,
-                            g.g0.w, g.g1.x, g.g1.w, 0u, 0u, (sc.flags & B2R_FLAG_NO_TILE_CULL) != 0, sc.width, sc.height,
-                            [&](int tx, int ty, uint32_t, uint32_t) { atomicAdd(tile_count + ty * gx + tx, 1u); });
+    aux.w = (int)warp_count_kept_tiles(visible, aux.x & 0xffff, aux.x >> 16, aux.y & 0xffff, aux.y >> 16, g.g0.x, g.g0.y,
+                                       g.g0.z, g.g0.w, g.g1.x, g.g1.w, (sc.flags & B2R_FLAG_NO_TILE_CULL) != 0, sc.width,
+                                       sc.height, gx, tile_count);
+    if (i < sc.P) cx.aux[i] = aux;
   }
   if (blockIdx.x == 0 && threadIdx.x == 0) cx.classes[CLS_SCAN_FINAL] = 0u;  // new counts: no final scan yet
   const unsigned vis = __ballot_sync(0xffffffffu, visible);
@@ -277,56 +278,56 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx, const int
     cx.tile_order[pos] = (uint32_t)t;
   }
   __syncthreads();
+  // Block-wide exclusive scan of ceil(n / 2^shift) over the first n_tiles entries of tile_order (all threads call it;
+  // the total is returned to every thread).  One pass of 1024 tiles covers every workload measured so far.
+  __shared__ uint32_t wsum[32];
+  auto scan_units = [&](const uint32_t n_tiles, const int shift, uint32_t* out) -> uint32_t {
+    uint32_t run = 0;
+    for (uint32_t base = 0; base < n_tiles; base += 1024) {
+      const uint32_t t = base + threadIdx.x;
+      uint32_t c = 0;
+      if (t < n_tiles) {
+        const uint2 r = cx.ranges[cx.tile_order[t]];
+        c = (r.y - r.x + (1u << shift) - 1u) >> shift;
+      }
+      uint32_t incl = c;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) {
+        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+        if (lane >= d) incl += v;
+      }
+      if (lane == 31) wsum[warp] = incl;
+      __syncthreads();
+      if (warp == 0) {
+        uint32_t w = wsum[lane];
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+          const uint32_t v = __shfl_up_sync(0xffffffffu, w, d);
+          if (lane >= d) w += v;
+        }
+        wsum[lane] = w;
+      }
+      __syncthreads();
+      if (t < n_tiles) out[t] = run + (warp > 0 ? wsum[warp - 1] : 0u) + incl - c;
+      run += wsum[31];
+      __syncthreads();  // wsum is rewritten by the next round
+    }
+    return run;
+  };
+  static_assert(SORT_CHUNK == 2048 && SEG == 256, "scan_units takes the unit as a shift");
   // Tiles of >= 2048 entries are sorted in chunks of SORT_CHUNK by separate CTAs and merged afterwards (binning.cu):
   // chunk_start[t] = first chunk of the t-th tile of tile_order, reserved[1] = number of chunks.
-  if (warp == 0) {
-    const uint32_t n_large = n_large_s;
-    uint32_t run = 0;
-    for (uint32_t base = 0; base < n_large; base += 32) {
-      const uint32_t t = base + lane;
-      uint32_t c = 0;
-      if (t < n_large) {
-        const uint2 r = cx.ranges[cx.tile_order[t]];
-        c = (r.y - r.x + SORT_CHUNK - 1) / SORT_CHUNK;
-      }
-      uint32_t incl = c;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
-      }
-      if (t < n_large) cx.chunk_start[t] = run + incl - c;
-      run += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) {
-      cx.status->reserved[1] = run;
-      cx.classes[CLS_N_CHUNKS] = run;
-    }
-    // Segment table of the multi-segment tiles (composite_fwd4.cu / composite_bwd4.cu): seg_start[t] = segments of all
-    // earlier such tiles = index of the tile's first checkpoint record.
-    const uint32_t n_multi = n_multi_s;
-    uint32_t segs = 0;
-    for (uint32_t base = 0; base < n_multi; base += 32) {
-      const uint32_t t = base + lane;
-      uint32_t c = 0;
-      if (t < n_multi) {
-        const uint2 r = cx.ranges[cx.tile_order[t]];
-        c = (r.y - r.x + SEG - 1) / SEG;
-      }
-      uint32_t incl = c;
-#pragma unroll
-      for (int d = 1; d < 32; d <<= 1) {
-        const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
-        if (lane >= d) incl += v;
-      }
-      if (t < n_multi) cx.seg_start[t] = segs + incl - c;
-      segs += __shfl_sync(0xffffffffu, incl, 31);
-    }
-    if (lane == 0) {
-      // cannot exceed the store by construction (sum of ceil(n / 256) <= capacity / 256 + tiles); guard all the same
-      if (segs > cx.max_segs) { segs = 0; cx.classes[CLS_N_MULTI] = 0; n_multi_s = 0; }
-      cx.classes[CLS_TOTAL_SEGS] = segs;
-    }
+  const uint32_t n_chunks = scan_units(n_large_s, 11, cx.chunk_start);
+  // Segment table of the multi-segment tiles (composite_fwd4.cu / composite_bwd4.cu): seg_start[t] = segments of all
+  // earlier such tiles = index of the tile's first checkpoint record.
+  uint32_t segs = scan_units(n_multi_s, 8, cx.seg_start);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    cx.status->reserved[1] = n_chunks;
+    cx.classes[CLS_N_CHUNKS] = n_chunks;
+    // cannot exceed the store by construction (sum of ceil(n / 256) <= capacity / 256 + tiles); guard all the same
+    if (segs > cx.max_segs) { segs = 0; cx.classes[CLS_N_MULTI] = 0; n_multi_s = 0; }
+    cx.classes[CLS_TOTAL_SEGS] = segs;
   }
   __syncthreads();
   for (uint32_t t = threadIdx.x; t < n_multi_s; t += blockDim.x) {  // one (tile, segment) entry per backward work item
