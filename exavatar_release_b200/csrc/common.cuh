@@ -206,35 +206,14 @@ __device__ __forceinline__ float region_max_p2(float sx, float sy, float A2, flo
 // and walked by all 32 lanes together, so one 144-tile scene splat no longer stalls 31 idle lanes behind it.  Must be
 // called by full warps.
 constexpr int KEPT_SMALL = 4;
+#ifndef WALK_COOP_COST_N
+#define WALK_COOP_COST_N 70  // tuning hook (build_ext.py B2R_NVCC_EXTRA); 0 = always cooperative above KEPT_SMALL
+#endif
+constexpr unsigned WALK_PRIVATE_COST = 45u, WALK_COOP_COST = WALK_COOP_COST_N;  // instructions per tile / per 32-tile round
 
 // tile index t (row-major inside a rect of width w) -> row; exact for the sizes that occur: (t + 0.5) / w is at least
 // 0.5 / w away from an integer, far more than the rounding of the reciprocal and the product
 __device__ __forceinline__ int rect_row(int t, float inv_w) { return (int)(((float)t + 0.5f) * inv_w); }
-
-// table[tile] += 1 for every lane with `has`, returning the value the lane's own increment saw (old value + rank).  Lanes of
-// a warp that hit the SAME counter are folded into one atomic: an avatar's mesh-ordered Gaussians put most lanes of a warp
-// into one or two tiles, and same-address atomics serialise (32-way per instruction, and across the warps and CTAs of the
-// SM: 2/3 of the aggregated scatter's duration on the C4 pass before this).  A few leader-election rounds, then whatever is
-// left (a warp of scattered scene splats) goes one atomic per lane, which is conflict-free there.  Full warps only.
-constexpr int AGG_ROUNDS = 3;
-__device__ __forceinline__ uint32_t warp_agg_add(uint32_t* table, bool has, int tile) {
-  const int lane = threadIdx.x & 31;
-  unsigned todo = __ballot_sync(0xffffffffu, has);
-  uint32_t res = 0u;
-  for (int round = 0; round < AGG_ROUNDS && todo; round++) {  // warp-uniform
-    const int leader = __ffs(todo) - 1;
-    const int lt = __shfl_sync(0xffffffffu, tile, leader);
-    const unsigned m = __ballot_sync(0xffffffffu, has && tile == lt) & todo;
-    uint32_t base = 0u;
-    if (lane == leader) base = atomicAdd(table + lt, (uint32_t)__popc(m));
-    base = __shfl_sync(0xffffffffu, base, leader);
-    if ((m >> lane) & 1u) res = base + (uint32_t)__popc(m & ((1u << lane) - 1u));
-    todo &= ~m;
-    if (round == 0 && m == (1u << leader)) break;  // nobody shares the first lane's tile: take the scattered route
-  }
-  if ((todo >> lane) & 1u) res = atomicAdd(table + tile, 1u);
-  return res;
-}
 
 // The counting walk (projection): table[ty * gx + tx] += 1 once per kept tile.  Returns, to the owner lane, the KEPT MASK
 // of a rect of at most 32 tiles (bit t = tile t in row-major order); the scatter replays it instead of repeating the
@@ -253,20 +232,25 @@ __device__ __forceinline__ uint32_t warp_count_kept_tiles(bool active, int x0, i
     return !(region_max_p2(sx, sy, a2, b2, c2, rx0, ry0, rx1, ry1) < th);
   };
   uint32_t kept = 0u;
-  const bool small = area > 0 && area <= KEPT_SMALL;
-  if (__any_sync(0xffffffffu, small)) {
+  // Schedule (warp-uniform): a lane walks its own rect (a region test per tile, ~45 instructions), or the rect is broadcast
+  // and the 32 lanes test 32 of its tiles at once (~70 instructions per round).  One large splat among small ones is
+  // cheaper shared; a warp of scene splats that all cover dozens of tiles is cheaper lane-private (32 rounds of 70 against
+  // max(area) rounds of 45).  The pairs are the same either way.
+  const bool big = area > KEPT_SMALL;
+  const unsigned coop_rounds = __reduce_add_sync(0xffffffffu, big ? (unsigned)((area + 31) >> 5) : 0u);
+  const unsigned max_area = __reduce_max_sync(0xffffffffu, (unsigned)area);
+  const bool all_private = max_area * WALK_PRIVATE_COST <= coop_rounds * WALK_COOP_COST + 64u;
+  if (area > 0 && (all_private || !big)) {
     int tx = x0, ty = y0;
-#pragma unroll
-    for (int t = 0; t < KEPT_SMALL; t++) {
-      const bool in = small && t < area;
-      const bool k = in && keep_tile(tx, ty, px, py, A2, B2, C2, thr2);
-      if (k) kept |= 1u << t;
-      const int tile = ty * gx + tx;
-      warp_agg_add(table, k, tile);
-      if (in && ++tx == x1) { tx = x0; ty++; }
+    for (int t = 0; t < area; t++) {
+      if (keep_tile(tx, ty, px, py, A2, B2, C2, thr2)) {
+        if (t < 32) kept |= 1u << t;
+        atomicAdd(table + ty * gx + tx, 1u);
+      }
+      if (++tx == x1) { tx = x0; ty++; }
     }
   }
-  unsigned mask = __ballot_sync(0xffffffffu, area > KEPT_SMALL);
+  unsigned mask = all_private ? 0u : __ballot_sync(0xffffffffu, big);
   while (mask) {
     const int src = __ffs(mask) - 1;
     mask &= mask - 1;
@@ -294,10 +278,11 @@ __device__ __forceinline__ uint32_t warp_count_kept_tiles(bool active, int x0, i
   return kept;
 }
 
-// The replay (scatter): the same (splat, tile) pairs as warp_count_kept_tiles produced.  Per pair: old = table[tile]++
-// (warp-aggregated like the count), then post(old, tile, u0, u1) with the owner's two payload words.  Rects of <= 32 tiles
-// come from the stored mask; only larger ones repeat the region test, so px..thr2 need to be valid on lanes whose rect has
-// more than 32 tiles only.  Must be called by full warps.
+// The replay (scatter): the same (splat, tile) pairs as warp_count_kept_tiles produced.  Per pair: old = table[tile]++,
+// then post(old, tile, u0, u1) with the owner's two payload words.  A rect of <= 32 tiles is replayed by its own lane from
+// the stored mask (a loop over the set bits: no shuffles, no region test; the warp pays the largest pair count among its
+// lanes, a handful).  Larger rects are walked by the 32 lanes together with the region test, so px..thr2 need to be valid
+// on lanes whose rect has more than 32 tiles only.  Must be called by full warps.
 template <typename F>
 __device__ __forceinline__ void warp_replay_kept_tiles(bool active, int x0, int y0, int x1, int y1, uint32_t kept, float px,
                                                        float py, float A2, float B2, float C2, float thr2, uint32_t u0,
@@ -306,20 +291,41 @@ __device__ __forceinline__ void warp_replay_kept_tiles(bool active, int x0, int 
   const int lane = threadIdx.x & 31;
   const int w = x1 - x0;
   const int area = active ? w * (y1 - y0) : 0;
-  const bool small = area > 0 && area <= KEPT_SMALL;
-  if (__any_sync(0xffffffffu, small)) {
-    int tx = x0, ty = y0;
-#pragma unroll
-    for (int t = 0; t < KEPT_SMALL; t++) {
-      const bool in = small && t < area;
-      const bool k = in && ((kept >> t) & 1u);
-      const int tile = ty * gx + tx;
-      const uint32_t old = warp_agg_add(table, k, tile);
-      if (k) post(old, tile, u0, u1);
-      if (in && ++tx == x1) { tx = x0; ty++; }
+  if (area > 0 && area <= 32) {
+    const float inv_w = __frcp_rn((float)w);
+    const int tile0 = y0 * gx + x0;
+    for (uint32_t m = kept; m; m &= m - 1u) {
+      const int t = __ffs(m) - 1;
+      const int r = rect_row(t, inv_w);
+      const int tile = tile0 + r * gx + (t - r * w);
+      post(atomicAdd(table + tile, 1u), tile, u0, u1);
     }
   }
-  unsigned mask = __ballot_sync(0xffffffffu, area > KEPT_SMALL);
+  const bool big = area > 32;
+  const unsigned coop_rounds = __reduce_add_sync(0xffffffffu, big ? (unsigned)((area + 31) >> 5) : 0u);
+  if (coop_rounds == 0u) return;
+  auto keep_tile = [&](int tx, int ty, float sx, float sy, float a2, float b2, float c2, float th) {
+    if (no_cull) return true;
+    const float rx0 = (float)(tx * TILE), ry0 = (float)(ty * TILE);
+    const float rx1 = fminf(rx0 + (float)(TILE - 1), (float)(W - 1));
+    const float ry1 = fminf(ry0 + (float)(TILE - 1), (float)(H - 1));
+    return !(region_max_p2(sx, sy, a2, b2, c2, rx0, ry0, rx1, ry1) < th);
+  };
+  const unsigned max_area = __reduce_max_sync(0xffffffffu, big ? (unsigned)area : 0u);
+  if (max_area * WALK_PRIVATE_COST <= coop_rounds * WALK_COOP_COST) {  // see warp_count_kept_tiles
+    if (big) {
+      int tx = x0, ty = y0;
+      for (int t = 0; t < area; t++) {
+        if (keep_tile(tx, ty, px, py, A2, B2, C2, thr2)) {
+          const int tile = ty * gx + tx;
+          post(atomicAdd(table + tile, 1u), tile, u0, u1);
+        }
+        if (++tx == x1) { tx = x0; ty++; }
+      }
+    }
+    return;
+  }
+  unsigned mask = __ballot_sync(0xffffffffu, big);
   while (mask) {
     const int src = __ffs(mask) - 1;
     mask &= mask - 1;
@@ -327,29 +333,13 @@ __device__ __forceinline__ void warp_replay_kept_tiles(bool active, int x0, int 
     const int bw = __shfl_sync(0xffffffffu, w, src), barea = __shfl_sync(0xffffffffu, area, src);
     const uint32_t s0 = __shfl_sync(0xffffffffu, u0, src), s1 = __shfl_sync(0xffffffffu, u1, src);
     const float inv_w = __frcp_rn((float)bw);
-    if (barea <= 32) {  // warp-uniform
-      const uint32_t skept = __shfl_sync(0xffffffffu, kept, src);
-      if ((skept >> lane) & 1u) {
-        const int r = rect_row(lane, inv_w);
-        const int tile = (by0 + r) * gx + bx0 + lane - r * bw;
-        post(atomicAdd(table + tile, 1u), tile, s0, s1);
-      }
-      continue;
-    }
     const float spx = __shfl_sync(0xffffffffu, px, src), spy = __shfl_sync(0xffffffffu, py, src);
     const float sA = __shfl_sync(0xffffffffu, A2, src), sB = __shfl_sync(0xffffffffu, B2, src);
     const float sC = __shfl_sync(0xffffffffu, C2, src), sT = __shfl_sync(0xffffffffu, thr2, src);
     for (int t = lane; t < barea; t += 32) {
       const int r = rect_row(t, inv_w);
       const int ty = by0 + r, tx = bx0 + t - r * bw;
-      bool k = true;
-      if (!no_cull) {
-        const float rx0 = (float)(tx * TILE), ry0 = (float)(ty * TILE);
-        const float rx1 = fminf(rx0 + (float)(TILE - 1), (float)(W - 1));
-        const float ry1 = fminf(ry0 + (float)(TILE - 1), (float)(H - 1));
-        k = !(region_max_p2(spx, spy, sA, sB, sC, rx0, ry0, rx1, ry1) < sT);
-      }
-      if (k) {
+      if (keep_tile(tx, ty, spx, spy, sA, sB, sC, sT)) {
         const int tile = ty * gx + tx;
         post(atomicAdd(table + tile, 1u), tile, s0, s1);
       }

@@ -47,7 +47,10 @@ __device__ __forceinline__ void sh_to_rgb(int deg, const float* __restrict__ sh,
   }
 }
 
-__global__ void __launch_bounds__(256) project_kernel(const B2RScene sc, const Ctx cx, int32_t* __restrict__ radii,
+#ifndef PROJ_MIN_BLOCKS
+#define PROJ_MIN_BLOCKS 4  // 64 registers: four CTAs per SM; tuning hook (build_ext.py B2R_NVCC_EXTRA)
+#endif
+__global__ void __launch_bounds__(256, PROJ_MIN_BLOCKS) project_kernel(const B2RScene sc, const Ctx cx, int32_t* __restrict__ radii,
                                                       const int aggregate) {
   // CTA-level histogram in shared memory: atomics of different warps to the SAME global address serialise in L2
   // (~15 ns each measured on the hot avatar tiles), so each CTA adds to a tile's counter at most once.

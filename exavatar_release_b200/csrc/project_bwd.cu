@@ -284,7 +284,10 @@ __device__ __forceinline__ void project_bwd_one(const B2RScene& sc, const Ctx& c
 // 128-byte lines per load instruction.  SH rows therefore move through shared memory: every warp copies the
 // contiguous block of its 32 rows in with coalesced 128-byte accesses (odd row stride: conflict-free), the body
 // turns each row into its gradient in place, and the warp writes (or accumulates) the block back the same way.
-__global__ void __launch_bounds__(256) project_bwd_kernel(const B2RScene sc, const Ctx cx, const B2RBackwardArgs out,
+#ifndef PBWD_MIN_BLOCKS
+#define PBWD_MIN_BLOCKS 3  // 80 registers (64 bytes spilled): three CTAs per SM measured faster than two at 116; tuning hook
+#endif
+__global__ void __launch_bounds__(256, PBWD_MIN_BLOCKS) project_bwd_kernel(const B2RScene sc, const Ctx cx, const B2RBackwardArgs out,
                                                           const float* __restrict__ gacc) {
   extern __shared__ float sh_stage[];
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
