@@ -923,7 +923,7 @@ def bench_single(env, args, wl, wl_key, brief=False):
     with torch.no_grad():
         for f in range(F):
             public_frame(f, grad=False)
-            dups.append(RZ._state(dev).predicted[(P, Wd, H)])
+            dups.append(RZ.last_duplicate_count(dev, P, Wd, H))
     cap = int(max(dups) * 1.1) + 4096
 
     S = max(1, min(args.lanes, F))

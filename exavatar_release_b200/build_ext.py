@@ -86,5 +86,37 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     return LIB
 
 
+TORCH_EXT = os.path.join(PKG, "_b2r_torch.so")
+TORCH_SRC = os.path.join(PKG, "csrc_torch", "b2r_torch.cpp")
+
+
+def build_torch_ext(force: bool = False, verbose: bool = False) -> str:
+    """The compiled torch binding of the eager path (csrc_torch/b2r_torch.cpp): host code only, g++ against the torch
+    headers of this interpreter, linked to libb200raster.so next to it (rpath $ORIGIN).  In-tree like the CUDA library."""
+    lib = build()
+    deps = [TORCH_SRC, os.path.join(PKG, "..", "include", "b200raster.h"), os.path.abspath(__file__)]
+    if not force and os.path.exists(TORCH_EXT) and os.path.getmtime(TORCH_EXT) > max(os.path.getmtime(d) for d in deps):
+        return TORCH_EXT
+    import sysconfig
+
+    import torch
+    from torch.utils.cpp_extension import include_paths, library_paths
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    incs = [*include_paths("cuda"), os.path.join(cuda_home, "include"), sysconfig.get_paths()["include"],
+            os.path.join(PKG, "..", "include")]
+    libdirs = [*library_paths("cuda"), os.path.join(cuda_home, "lib64"), PKG]
+    cmd = [os.environ.get("CXX", "g++"), "-O2", "-std=c++17", "-fPIC", "-shared", "-DTORCH_EXTENSION_NAME=_b2r_torch",
+           "-DTORCH_API_INCLUDE_EXTENSION_H", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           *[f"-I{os.path.abspath(i)}" for i in dict.fromkeys(incs)], TORCH_SRC, "-o", TORCH_EXT,
+           *[f"-L{os.path.abspath(d)}" for d in dict.fromkeys(libdirs)], "-lc10", "-lc10_cuda", "-ltorch_cpu", "-ltorch_cuda",
+           "-ltorch", "-ltorch_python", "-lcudart", f"-l:{os.path.basename(lib)}", "-Wl,-rpath,$ORIGIN",
+           *[f"-Wl,-rpath,{os.path.abspath(d)}" for d in library_paths("cuda")]]
+    if verbose:
+        print(" ".join(cmd), flush=True)
+    subprocess.check_call(cmd)
+    return TORCH_EXT
+
+
 if __name__ == "__main__":
     build(force=True, verbose=True, ptxas_info="--ptxas" in sys.argv)
+    build_torch_ext(force=True, verbose=True)

@@ -345,7 +345,50 @@ class _RasterizeGaussians(torch.autograd.Function):
                 d_scales if has_sc else None, d_rots if has_rot else None, d_cov if has_cov else None, None)
 
 
+# The compiled binding of this call (csrc_torch/b2r_torch.cpp, built by build_ext.build_torch_ext): the same host logic
+# as _RasterizeGaussians / _forward_impl / _backward_impl as a C++ autograd Function over the same C ABI -- it removes
+# ~0.2 ms of Python per render from the eager path.  B2R_COMPILED_BINDING=0 keeps the Python route (also used for
+# debug=True, fixed-capacity / graph capture and when the extension has not been built).
+COMPILED_BINDING = os.environ.get("B2R_COMPILED_BINDING", "1") != "0"
+_COMPILED = None
+
+
+def _compiled_binding():
+    global _COMPILED
+    if _COMPILED is None:
+        _COMPILED = False
+        path = os.path.join(os.path.dirname(os.path.abspath(__file__)), "_b2r_torch.so")
+        if COMPILED_BINDING and os.path.exists(path):
+            import importlib.util
+            L.load()  # libb200raster.so first: the extension links against it
+            spec = importlib.util.spec_from_file_location("_b2r_torch", path)
+            mod = importlib.util.module_from_spec(spec)
+            spec.loader.exec_module(mod)
+            if mod.abi_version() != L.ABI_VERSION:
+                raise RuntimeError("b200raster: _b2r_torch.so was built against another ABI version; rebuild it")
+            _COMPILED = mod
+    return _COMPILED
+
+
+def last_duplicate_count(device: torch.device, P: int, W: int, H: int) -> int:
+    """Duplicate count of the most recent adaptive-capacity render of this shape on `device` (whichever host route ran
+    it); KeyError when there was none.  Callers size fixed-capacity plans with it."""
+    ext = _compiled_binding()
+    idx = device.index if device.index is not None else torch.cuda.current_device()
+    n = ext.get_predicted(idx, P, W, H) if ext else -1
+    if n >= 0:
+        return int(n)
+    return int(_state(device).predicted[(P, W, H)])
+
+
 def rasterize_gaussians(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp, raster_settings):
+    st = raster_settings
+    ext = _compiled_binding() if (FIXED_CAPACITY is None and not st.debug) else False
+    if ext:
+        return tuple(ext.rasterize(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
+                                   int(st.image_height), int(st.image_width), float(st.tanfovx), float(st.tanfovy), st.bg,
+                                   float(st.scale_modifier), st.viewmatrix, st.projmatrix, int(st.sh_degree), st.campos,
+                                   TILE_CULL, CAPACITY_MODE == "speculative", CAPACITY_HEADROOM, SEGMENTED))
     return _RasterizeGaussians.apply(means3D, means2D, sh, colors_precomp, opacities, scales, rotations, cov3Ds_precomp,
                                      raster_settings)
 

@@ -202,3 +202,18 @@ def test_error_codes_of_the_abi_v3_entry_points_without_touching_cuda():
     args.dL_dposed = fake                    # a posed-position gradient only makes sense with fused skinning
     assert bp(fake, 1 << 20) == -1
     assert lib.b2r_backward(C.byref(sc), C.byref(ws), C.byref(args), fake, 1 << 20, None) == -1
+
+
+def test_compiled_torch_binding_builds_and_loads():
+    """csrc_torch/b2r_torch.cpp (the eager call's host path as a C++ autograd Function) builds in-tree against this
+    interpreter's torch, links to libb200raster.so and reports the same ABI version.  No compute here (no GPU)."""
+    from exavatar_release_b200 import build_ext, rasterizer
+    path = build_ext.build_torch_ext()
+    assert os.path.exists(path)
+    ext = rasterizer._compiled_binding()
+    assert ext and ext.abi_version() == L.ABI_VERSION
+    import torch
+    a = torch.zeros(4, 3)
+    with pytest.raises(RuntimeError, match="CUDA tensor"):  # no CPU fallback in the compiled route either
+        ext.rasterize(a, a, None, a, torch.zeros(4, 1), a, torch.zeros(4, 4), None, 16, 16, 1.0, 1.0, torch.zeros(3), 1.0,
+                      torch.eye(4), torch.eye(4), 0, torch.zeros(3), True, True, 1.25, True)

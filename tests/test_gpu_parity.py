@@ -278,6 +278,76 @@ def test_cov3d_precomp_path(dev):
     _check("d_means3D", m3.grad.cpu().numpy(), og["means3D"], np.broadcast_to(gm[:, None], og["means3D"].shape), max_bad_frac=0.2)
 
 
+@pytest.mark.parametrize("case", ["rgb", "sh", "cov", "depth_alpha_only", "noncontiguous"])
+def test_compiled_binding_equals_python_route(dev, monkeypatch, case):
+    """The C++ autograd Function (csrc_torch/b2r_torch.cpp) and the Python one (_RasterizeGaussians) are two hosts of the
+    same kernels: identical forward outputs bit for bit, gradients equal up to the order of the backward's atomic sums,
+    None exactly where the other route returns None."""
+    rz = RZ()
+    assert rz._compiled_binding(), "the compiled binding (_b2r_torch.so) must be built: python -m exavatar_release_b200.build_ext"
+    wl = "T2" if case == "sh" else "T1"
+    st = workload_settings(wl, yaw=9.0, device=dev, settings_cls=rz.GaussianRasterizationSettings)
+    if case == "sh":
+        st = st._replace(sh_degree=3)
+    if case == "noncontiguous":  # module.py:605-606 hands over transposed views
+        st = st._replace(viewmatrix=st.viewmatrix.t().contiguous().t(), projmatrix=st.projmatrix.t().contiguous().t())
+        assert not st.viewmatrix.is_contiguous()
+    a0 = make_assets(wl, seed=3)
+    P = a0["mean_3d"].shape[0]
+    if case == "cov":
+        g = torch.Generator().manual_seed(5)
+        A = torch.randn(P, 3, 3, generator=g) * 0.05
+        S = A @ A.transpose(1, 2) + 1e-4 * torch.eye(3)
+        a0 = dict(a0, cov=torch.stack([S[:, 0, 0], S[:, 0, 1], S[:, 0, 2], S[:, 1, 1], S[:, 1, 2], S[:, 2, 2]], 1))
+    gi = make_grad_image(wl, 4).to(dev)
+
+    def run(compiled):
+        monkeypatch.setattr(rz, "_COMPILED", rz._compiled_binding() if compiled else False)
+        a = {k: v.to(dev).requires_grad_() for k, v in a0.items()}
+        m2 = torch.zeros(P, 3, device=dev, requires_grad=True)
+        kw = dict(means3D=a["mean_3d"], means2D=m2, opacities=a["opacity"])
+        if case == "sh":
+            kw.update(shs=a["shs"], scales=a["scale"], rotations=a["rotation"])
+        elif case == "cov":
+            kw.update(colors_precomp=a["rgb"], cov3D_precomp=a["cov"])
+        else:
+            kw.update(colors_precomp=a["rgb"], scales=a["scale"], rotations=a["rotation"])
+        out = rz.GaussianRasterizer(st)(**kw)
+        color, radii, depth, alpha = out
+        if case == "depth_alpha_only":
+            loss = (depth * gi[:1]).sum() + (alpha * gi[1:2]).sum()
+        elif case == "rgb":
+            loss = (color * gi).sum() + 0.3 * (depth * gi[:1]).sum()
+        else:
+            loss = (color * gi).sum()
+        loss.backward()
+        return [t.detach() for t in out], {k: v.grad for k, v in a.items()}, m2.grad
+
+    o_c, g_c, m_c = run(True)
+    o_p, g_p, m_p = run(False)
+    for x, y in zip(o_c, o_p):
+        assert torch.equal(x, y)
+    close = lambda x, y: torch.allclose(x, y, rtol=1e-4, atol=1e-5 * float(y.abs().max()) + 1e-12)
+    for k in g_p:
+        assert (g_c[k] is None) == (g_p[k] is None), k
+        if g_p[k] is not None:
+            assert g_c[k].shape == g_p[k].shape and close(g_c[k], g_p[k]), k
+    assert close(m_c, m_p)
+
+
+def test_compiled_binding_handles_an_empty_call(dev):
+    rz = RZ()
+    assert rz._compiled_binding()
+    st = workload_settings("T0", yaw=0.0, device=dev, settings_cls=rz.GaussianRasterizationSettings)
+    z = lambda *s: torch.zeros(*s, device=dev, requires_grad=True)
+    m3, op = z(0, 3), z(0, 1)
+    color, radii, depth, alpha = rz.GaussianRasterizer(st)(means3D=m3, means2D=z(0, 3), opacities=op, colors_precomp=z(0, 3),
+                                                           scales=z(0, 3), rotations=z(0, 4))
+    assert float(color.abs().max()) == 0.0 and radii.numel() == 0
+    color.sum().backward()
+    assert m3.grad.shape == (0, 3) and op.grad.shape == (0, 1)
+
+
 def test_five_live_contexts_then_one_backward(dev):
     """ExAvatar renders five asset sets before the single loss.backward() (model.py:130-162, train.py:46)."""
     rz = RZ()
@@ -302,8 +372,13 @@ def test_five_live_contexts_then_one_backward(dev):
         assert torch.allclose(m2.grad, m2b.grad, rtol=1e-4, atol=1e-4 * float(m2b.grad.abs().max()))
 
 
-def test_forward_is_deterministic_and_capacity_modes_agree(dev, monkeypatch):
+@pytest.mark.parametrize("route", ["compiled", "python"])
+def test_forward_is_deterministic_and_capacity_modes_agree(dev, monkeypatch, route):
     rz = RZ()
+    if route == "python":
+        monkeypatch.setattr(rz, "_COMPILED", False)
+    else:
+        assert rz._compiled_binding(), "the compiled binding (_b2r_torch.so) must be built: python -m exavatar_release_b200.build_ext"
     st = workload_settings("T1", yaw=12.0, device=dev, settings_cls=rz.GaussianRasterizationSettings)
     a = {k: v.to(dev) for k, v in make_assets("T1", seed=0).items()}
     P = a["mean_3d"].shape[0]
@@ -323,6 +398,8 @@ def test_forward_is_deterministic_and_capacity_modes_agree(dev, monkeypatch):
         assert torch.equal(x, y)
     # a misprediction (capacity far too small) must be repaired transparently
     rz._state(dev).predicted[(P, st.image_width, st.image_height)] = 10
+    if route == "compiled":
+        rz._compiled_binding().set_predicted(dev.index, P, st.image_width, st.image_height, 10)
     monkeypatch.setattr(rz, "CAPACITY_HEADROOM", 1.0)
     small = render()
     for x, y in zip(ref, small):

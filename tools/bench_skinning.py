@@ -61,7 +61,7 @@ def main():
     with torch.no_grad():
         RZ.GaussianRasterizer(st)(means3D=human["mean_3d"], means2D=torch.zeros(P, 3, device=dev), opacities=human["opacity"],
                                   colors_precomp=human["rgb"], scales=human["scale"], rotations=human["rotation"])
-    cap = int(RZ._state(dev).predicted[(P, W, H)] * 1.3) + 4096
+    cap = int(RZ.last_duplicate_count(dev, P, W, H) * 1.3) + 4096
     RZ.set_fixed_capacity(cap)
     out, out_graph = {}, {}
     for name, fn in (("unfused", unfused), ("fused", fused)):
