@@ -34,8 +34,8 @@ struct B4Stage {
   float4 c[B4_BATCH];  // r, g, b, id | clamp bits << 29
 };
 constexpr int B4_GROUP = 4;   // splats replayed per trip of the hit loop (their evaluations overlap: ILP 4)
-constexpr int B4_CQ = 36;     // survivor queue: <= 3 left over + 32 new per chunk (+ pad)
-struct B4Compact {            // warp-private queue of cull survivors, back to front
+constexpr int B4_CQ = 32 + B4_GROUP;  // circular survivor queue: < B4_GROUP left over + 32 new per chunk; a multiple of B4_GROUP
+struct B4Compact {            // warp-private circular queue of cull survivors, back to front
   float4 r[3][B4_CQ];         // [0] px,py,A2,B2  [1] C2,opacity,depth,list position (int bits)  [2] r,g,b,id bits
 };
 static_assert(B4_QUEUE % B4_GROUP == 0, "phase B runs when whole groups fill the transposition queue");
@@ -218,11 +218,18 @@ __device__ __forceinline__ void bwd4_item(const B2RScene& sc, const Ctx& cx, con
   };
 
   const uint32_t id_begin = cx.id_begin, id_span = cx.id_span;
-  auto issue = [&](int b) {
+  // list entry -> record is two dependent global loads: the entry of the batch after next is fetched into a register while
+  // the current batch is replayed (see composite_fwd4.cu)
+  uint32_t next_id = 0u;
+  auto prefetch = [&](int b) {
+    const int idx = b * B4_BATCH + threadIdx.x;
+    next_id = idx < nmax ? __ldg(ids + idx) : 0u;
+  };
+  auto issue = [&](int b) {  // consumes next_id (= the entry of batch b)
     B4Stage& s = stage[b & 1];
     const int idx = b * B4_BATCH + threadIdx.x;
     if (idx < nmax) {
-      const uint32_t id = __ldg(ids + idx);
+      const uint32_t id = next_id;
       if (id - id_begin < id_span) {
         const float4* src = reinterpret_cast<const float4*>(cx.geom + id);
         cp_async16(&s.a[threadIdx.x], src);
@@ -276,12 +283,17 @@ __device__ __forceinline__ void bwd4_item(const B2RScene& sc, const Ctx& cx, con
     }
   };
 
-  int fill = 0;  // warp-uniform: survivors waiting in the queue (< B4_GROUP between chunks)
+  int head = 0, fill = 0;  // warp-uniform: slot of the oldest queued survivor (a multiple of B4_GROUP); survivors queued
+  prefetch(nb - 1);
   issue(nb - 1);
+  if (nb > 1) prefetch(nb - 2);
   for (int b = nb - 1; b >= 0; b--) {
     cp_async_wait<0>();
     __syncthreads();  // batch b staged; both warps are done with batch b+1
-    if (b > 0) issue(b - 1);
+    if (b > 0) {
+      issue(b - 1);
+      if (b > 1) prefetch(b - 2);
+    }
     const int count = min(B4_BATCH, nmax - b * B4_BATCH);
     const B4Stage& s = stage[b & 1];
     if (warp_n <= b * B4_BATCH) continue;  // warp-uniform: none of my pixels reaches this batch
@@ -298,34 +310,30 @@ __device__ __forceinline__ void bwd4_item(const B2RScene& sc, const Ctx& cx, con
       const unsigned mask = __ballot_sync(0xffffffffu, hit);
       if (mask == 0u) continue;
       if (hit) {  // back to front: the highest surviving list position is queued first
-        const int slot = fill + __popc(mask & lanes_above);
+        int slot = head + fill + __popc(mask & lanes_above);
+        slot -= slot >= B4_CQ ? B4_CQ : 0;
         cw.r[0][slot] = a;
         cw.r[1][slot] = make_float4(bb.x, bb.y, bb.z, __int_as_float(pos));
         cw.r[2][slot] = s.c[idx];
       }
       fill += __popc(mask);
       __syncwarp();
-      int k = 0;
-      for (; k + B4_GROUP <= fill; k += B4_GROUP) replay_group(k);
-      const int left = fill - k;
-      __syncwarp();
-      if (k > 0 && lane < 3 * left) {  // move the <= 3 leftover records to the front (sources are slots >= 4)
-        const int t = (lane >= left) + (lane >= 2 * left), j = lane - t * left;
-        cw.r[t][j] = cw.r[t][k + j];
+      for (; fill >= B4_GROUP; fill -= B4_GROUP) {  // what does not fill a group stays queued where it is
+        replay_group(head);
+        head = head + B4_GROUP == B4_CQ ? 0 : head + B4_GROUP;
       }
-      fill = left;
-      __syncwarp();  // queue reads / moves before the next append
+      __syncwarp();  // queue reads before the next append
     }
   }
   if (fill > 0) {  // flush: pad the last group with splats that can never be valid (list position INT_MAX); their
                    // opacity is 1 because phase B divides by it
-    if (lane >= fill && lane < B4_GROUP) {
-      cw.r[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-      cw.r[1][lane] = make_float4(0.f, 1.f, 0.f, __int_as_float(0x7fffffff));
-      cw.r[2][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane >= fill && lane < B4_GROUP) {  // head is a multiple of B4_GROUP: the group does not wrap
+      cw.r[0][head + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cw.r[1][head + lane] = make_float4(0.f, 1.f, 0.f, __int_as_float(0x7fffffff));
+      cw.r[2][head + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
-    replay_group(0);
+    replay_group(head);
   }
   if (qpos > 0) drain(qpos);
   if (threadIdx.x == 0) atomicAdd(reinterpret_cast<unsigned long long*>(&cx.status->consumed_bwd), (unsigned long long)nmax);

@@ -33,21 +33,32 @@ namespace b2r {
 #define FL_BATCH_N 128  // entries staged per batch (tuning hook; 64 measured in profiles/r02_notes.md)
 #endif
 constexpr int F4_BATCH = 2 * FL_BATCH_N;  // capacity of the two-half staging buffer
-constexpr int F4_GROUP = 4;    // splats blended per trip of the hit loop (their evaluations overlap: ILP 4)
-constexpr int F4_CQ = 36;      // survivor queue: <= 3 left over + 32 new per chunk (+ pad)
+#ifndef F4_GROUP_N
+#define F4_GROUP_N 4
+#endif
+constexpr int F4_GROUP = F4_GROUP_N;  // splats blended per trip of the hit loop (their evaluations overlap: ILP 4)
+constexpr int F4_CQ = 32 + F4_GROUP;  // circular survivor queue: < F4_GROUP left over + 32 new per chunk; a multiple of
+                                      // F4_GROUP, so a group never straddles the wrap
 
 struct F4Stage {
   float4 a[F4_BATCH];  // px, py, A2, B2
   float4 b[F4_BATCH];  // C2, opacity, depth, thr2
   float4 c[F4_BATCH];  // r, g, b, id bits
 };
-struct F4Queue {          // warp-private queue of cull survivors in list order
+struct F4Queue {          // warp-private circular queue of cull survivors in list order
   float4 r[3][F4_CQ];     // [0] px,py,A2,B2  [1] C2,opacity,depth,1-based list position (int bits)  [2] r,g,b,-
 };
-struct Blend {            // per-pixel blend state; T < 0 marks a finished pixel (|T| is still the transmittance)
-  float T, Cr, Cg, Cb, Dp, Aa;
+// Per-pixel blend state.  T is the RUNNING PRODUCT of (1 - alpha) over every splat the pixel accepted or was stopped by:
+// it is multiplied unconditionally, so the only serial dependency between consecutive splats is one FMUL (round 1 carried
+// "finished" in the sign of T, which put a compare, a predicate combine and a select on that chain: ~18 cycles per splat
+// for a warp that runs alone).  A pixel is alive while T >= 1e-4; the first accepted splat that takes the product below
+// 1e-4 finishes the pixel without being applied (App. A.3), and because the product can only shrink, nothing after it
+// passes `T_next >= 1e-4` again.  Tf trails T: the transmittance after the last APPLIED splat = App. A.3's final_T.
+struct Blend {
+  float T, Tf, Cr, Cg, Cb, Dp, Aa;
   uint32_t last;
 };
+__device__ __forceinline__ bool alive(const Blend& s) { return s.T >= K_T_MIN; }
 
 __device__ __forceinline__ void store4v(float* base, bool vec_ok, int lane, float v, bool inside) {
   if (vec_ok) {
@@ -65,7 +76,7 @@ __device__ __forceinline__ void store4v(float* base, bool vec_ok, int lane, floa
 // (App. A.3): a splat is skipped unless the pixel is alive, power <= 0 and alpha >= 1/255; a splat that would drop the
 // transmittance below 1e-4 finishes the pixel WITHOUT being applied.
 __device__ __forceinline__ void blend_group4(const F4Queue& cw, const int k, Blend& s, const float pxf, const float pyf) {
-  float al[F4_GROUP];
+  float al[F4_GROUP], om[F4_GROUP];
   bool ok[F4_GROUP];
   float4 col[F4_GROUP];
   float dep[F4_GROUP];
@@ -79,30 +90,33 @@ __device__ __forceinline__ void blend_group4(const F4Queue& cw, const int k, Ble
     const float ar = bb.y * ex2_approx(p2);
     al[u] = fminf(K_ALPHA_MAX, ar);
     ok[u] = (ar >= K_ALPHA_MIN) & (p2 <= 0.f);
+    om[u] = ok[u] ? 1.f - al[u] : 1.f;  // a splat the pixel skips leaves the product alone
     dep[u] = bb.z;
     pos[u] = (uint32_t)__float_as_int(bb.w);
   }
 #pragma unroll
   for (int u = 0; u < F4_GROUP; u++) {
-    const bool v = ok[u] & (s.T > 0.f);
-    const float test = s.T * (1.f - al[u]);
     const float w = al[u] * s.T;
-    const bool stop = v & (test < K_T_MIN);
-    const bool use = v & !stop;
+    const float Tn = s.T * om[u];              // the whole serial chain: one multiply per splat
+    const bool use = ok[u] & (Tn >= K_T_MIN);  // false for ever once the product has dropped below 1e-4
     s.Cr = use ? fmaf(col[u].x, w, s.Cr) : s.Cr;  // predicated accumulates: a skipped splat must not touch the sums at all
     s.Cg = use ? fmaf(col[u].y, w, s.Cg) : s.Cg;
     s.Cb = use ? fmaf(col[u].z, w, s.Cb) : s.Cb;
     s.Dp = use ? fmaf(dep[u], w, s.Dp) : s.Dp;
     s.Aa = use ? s.Aa + w : s.Aa;
     s.last = use ? pos[u] : s.last;
-    s.T = use ? test : (stop ? -s.T : s.T);
+    s.Tf = use ? Tn : s.Tf;
+    s.T = Tn;
   }
 }
 
 // 32 staged entries (one per lane; `in_range` false past the end): sub-tile cull against the warp's 8x4 rect, survivors
-// appended to the queue in list order, whole groups blended.  `pos1` = 1-based list position of this lane's entry.
+// appended to the circular queue in list order, whole groups blended.  `head` = slot of the oldest queued survivor (a
+// multiple of F4_GROUP), `fill` = survivors queued; what does not fill a group simply stays where it is (round 1 moved
+// the leftovers to the front after every chunk: 19 instructions and two warp barriers per chunk).  `pos1` = 1-based list
+// position of this lane's entry.
 __device__ __forceinline__ void cull_and_blend(const F4Stage& st, const int idx, const bool in_range, const int pos1,
-                                               F4Queue& cw, int& fill, Blend& s, const float rx0, const float ry0,
+                                               F4Queue& cw, int& head, int& fill, Blend& s, const float rx0, const float ry0,
                                                const float rx1, const float ry1, const float pxf, const float pyf) {
   const int lane = threadIdx.x & 31;
   bool hit = false;
@@ -115,51 +129,46 @@ __device__ __forceinline__ void cull_and_blend(const F4Stage& st, const int idx,
   const unsigned mask = __ballot_sync(0xffffffffu, hit);
   if (mask == 0u) return;
   if (hit) {
-    const int slot = fill + __popc(mask & ((1u << lane) - 1u));
+    int slot = head + fill + __popc(mask & ((1u << lane) - 1u));
+    slot -= slot >= F4_CQ ? F4_CQ : 0;
     cw.r[0][slot] = a;
     cw.r[1][slot] = make_float4(bb.x, bb.y, bb.z, __int_as_float(pos1));
     cw.r[2][slot] = st.c[idx];
   }
   fill += __popc(mask);
   __syncwarp();
-  int k = 0;
-  for (; k + F4_GROUP <= fill; k += F4_GROUP) blend_group4(cw, k, s, pxf, pyf);
-  const int left = fill - k;
-  if (k > 0) {  // move the <= 3 leftover records to the front (sources are slots >= 4: no overlap)
-    __syncwarp();
-    if (lane < 3 * left) {
-      const int t = (lane >= left) + (lane >= 2 * left), j = lane - t * left;
-      cw.r[t][j] = cw.r[t][k + j];
-    }
+  for (; fill >= F4_GROUP; fill -= F4_GROUP) {
+    blend_group4(cw, head, s, pxf, pyf);
+    head = head + F4_GROUP == F4_CQ ? 0 : head + F4_GROUP;
   }
-  fill = left;
-  __syncwarp();  // orders the queue reads / moves before the next append
+  __syncwarp();  // orders the queue reads before the next append
 }
 
 // blends what is still queued: the last group is padded with splats of opacity 0 (alpha 0 < 1/255 => skipped)
-__device__ __forceinline__ void flush_queue(F4Queue& cw, int& fill, Blend& s, const float pxf, const float pyf) {
+__device__ __forceinline__ void flush_queue(F4Queue& cw, int& head, int& fill, Blend& s, const float pxf, const float pyf) {
   if (fill > 0) {
     const int lane = threadIdx.x & 31;
-    if (lane >= fill && lane < F4_GROUP) {
-      cw.r[0][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-      cw.r[1][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
-      cw.r[2][lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (lane >= fill && lane < F4_GROUP) {  // head is a multiple of F4_GROUP: the group does not wrap
+      cw.r[0][head + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cw.r[1][head + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
+      cw.r[2][head + lane] = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncwarp();
-    blend_group4(cw, 0, s, pxf, pyf);
+    blend_group4(cw, head, s, pxf, pyf);
     __syncwarp();
+    head = head + F4_GROUP == F4_CQ ? 0 : head + F4_GROUP;
     fill = 0;
   }
 }
 
 __device__ __forceinline__ void store_checkpoint(float* rec, const int pix_in_tile, const Blend& s) {
-  reinterpret_cast<float4*>(rec)[pix_in_tile] = make_float4(fabsf(s.T), s.Cr, s.Cg, s.Cb);
+  reinterpret_cast<float4*>(rec)[pix_in_tile] = make_float4(s.Tf, s.Cr, s.Cg, s.Cb);
   reinterpret_cast<float2*>(rec + CK_PLANE0)[pix_in_tile] = make_float2(s.Dp, s.Aa);
 }
 
 __device__ __forceinline__ void write_outputs(const B2RScene& sc, const Ctx& cx, const B2RForwardOutputs& out, const int vec_ok,
                                               const Blend& S, const int px, const int py, const bool inside, const int lane) {
-  const float T = fabsf(S.T);
+  const float T = S.Tf;
   const size_t N = (size_t)sc.width * sc.height;
   const size_t pix = (size_t)py * sc.width + px;
   const float* bgp = cx.bg ? cx.bg : sc.bg;
@@ -179,7 +188,7 @@ constexpr int FL_BATCH = FL_BATCH_N;
 static_assert(SEG % FL_BATCH == 0, "checkpoint cuts fall on batch boundaries");
 
 #ifndef F4_MIN_BLOCKS
-#define F4_MIN_BLOCKS 1  // tuning hook: 16 forces <= 64 registers (measured, profiles/r02_notes.md)
+#define F4_MIN_BLOCKS 14  // = the shared-memory limit (15.7 KB per CTA): keeps the kernel at 72 registers; 16 forces 64 (measured)
 #endif
 __global__ void __launch_bounds__(FL_THREADS, F4_MIN_BLOCKS) composite_fwd_kernel(const B2RScene sc, const Ctx cx,
                                                                           const B2RForwardOutputs out, const int vec_ok) {
@@ -211,14 +220,27 @@ __global__ void __launch_bounds__(FL_THREADS, F4_MIN_BLOCKS) composite_fwd_kerne
   if (cx.ckpt && t_pos < (int)cx.classes[CLS_N_MULTI]) ck = cx.ckpt + (size_t)cx.seg_start[t_pos] * CK_REC_FLOATS;
 
   const uint32_t id_begin = cx.id_begin, id_span = cx.id_span;
-  auto issue = [&](int b) {
+  // The gather of a batch is two dependent global loads (list entry -> record).  The list entries of batch b+2 are
+  // fetched into registers while batch b is composited, so that issue(b+1) starts its record gathers without waiting for
+  // them (ncu source page of the thin views, profiles/r02_notes.md: a quarter of the stall samples sat on that wait, and
+  // the partner warp's share of it at the batch barrier).
+  constexpr int FL_PER_THREAD = FL_BATCH / FL_THREADS;
+  uint32_t next_id[FL_PER_THREAD];
+  auto prefetch = [&](int b) {
+#pragma unroll
+    for (int u = 0; u < FL_PER_THREAD; u++) {
+      const int idx = b * FL_BATCH + threadIdx.x + u * FL_THREADS;
+      next_id[u] = idx < n ? __ldg(ids + idx) : 0u;
+    }
+  };
+  auto issue = [&](int b) {  // consumes next_id (= the entries of batch b)
     const int half = (b & 1) * FL_BATCH;
 #pragma unroll
-    for (int u = 0; u < FL_BATCH / FL_THREADS; u++) {
+    for (int u = 0; u < FL_PER_THREAD; u++) {
       const int slot = half + threadIdx.x + u * FL_THREADS;
       const int idx = b * FL_BATCH + threadIdx.x + u * FL_THREADS;
       if (idx < n) {
-        const uint32_t id = __ldg(ids + idx);
+        const uint32_t id = next_id[u];
         if (id - id_begin < id_span) {
           const float4* src = reinterpret_cast<const float4*>(cx.geom + id);
           cp_async16(&stage_raw.a[slot], src);
@@ -234,31 +256,38 @@ __global__ void __launch_bounds__(FL_THREADS, F4_MIN_BLOCKS) composite_fwd_kerne
   };
 
   Blend S;
-  S.T = inside ? 1.f : -1.f;
+  S.T = S.Tf = inside ? 1.f : 0.f;
   S.Cr = S.Cg = S.Cb = S.Dp = S.Aa = 0.f;
   S.last = 0;
   F4Queue& cw = queue[warp];
-  int fill = 0, staged = 0;
-  if (nb > 0) issue(0);
+  int head = 0, fill = 0, staged = 0;
+  if (nb > 0) {
+    prefetch(0);
+    issue(0);
+    if (nb > 1) prefetch(1);
+  }
   for (int b = 0; b < nb; b++) {
     cp_async_wait<0>();
-    if (__syncthreads_and(!(S.T > 0.f))) break;  // batch b visible; everyone is past batch b-1
-    if (b + 1 < nb) issue(b + 1);
+    if (__syncthreads_and(!alive(S))) break;  // batch b visible; everyone is past batch b-1
+    if (b + 1 < nb) {
+      issue(b + 1);
+      if (b + 2 < nb) prefetch(b + 2);
+    }
     const int count = min(FL_BATCH, n - b * FL_BATCH);
     staged += count;
     const int half = (b & 1) * FL_BATCH;
-    bool warp_live = __any_sync(0xffffffffu, S.T > 0.f);
+    bool warp_live = __any_sync(0xffffffffu, alive(S));
     for (int c0 = 0; c0 < count && warp_live; c0 += 32) {
       const int idx = c0 + lane;
-      cull_and_blend(stage_raw, half + idx, idx < count, b * FL_BATCH + idx + 1, cw, fill, S, rx0, ry0, rx1, ry1, pxf, pyf);
-      warp_live = __any_sync(0xffffffffu, S.T > 0.f);
+      cull_and_blend(stage_raw, half + idx, idx < count, b * FL_BATCH + idx + 1, cw, head, fill, S, rx0, ry0, rx1, ry1, pxf, pyf);
+      warp_live = __any_sync(0xffffffffu, alive(S));
     }
     if (ck && ((b + 1) * FL_BATCH) % SEG == 0 && b + 1 < nb) {  // a cut (multiple of 256): the state must be exact there
-      flush_queue(cw, fill, S, pxf, pyf);
+      flush_queue(cw, head, fill, S, pxf, pyf);
       if (inside) store_checkpoint(ck + (size_t)((b + 1) * FL_BATCH / SEG - 1) * CK_REC_FLOATS, pix_in_tile, S);
     }
   }
-  flush_queue(cw, fill, S, pxf, pyf);
+  flush_queue(cw, head, fill, S, pxf, pyf);
   cp_async_wait<0>();
   if (ck && nrec >= 2 && inside) store_checkpoint(ck + (size_t)(nrec - 1) * CK_REC_FLOATS, pix_in_tile, S);
   // consumed_fwd counts list entries per TILE x 8: four quarter-CTAs each add twice what they staged
