@@ -28,17 +28,22 @@ constexpr float CULL_MARGIN2 = 0.02f;
 constexpr int SORT_CHUNK = 2048;  // per-tile sort: lists are sorted in chunks of this many entries (binning.cu)
 // Segmented composites (composite_fwd4.cu / composite_bwd4.cu).  A tile's depth-sorted list is cut every SEG entries;
 // the forward stores the per-pixel blend state at every cut (a "checkpoint record"), which lets the backward replay
-// each (quarter tile, segment) as an independent work item, and lists of >= HEAVY_MIN entries are blended by eight
-// warps per 8x4 pixel rect in the forward.  SEG is also the forward's staging batch, so cuts are batch boundaries.
-constexpr int SEG = 256;
-constexpr int HEAVY_MIN = 512;
+// each (quarter tile, segment) as an independent work item.  SEG is a multiple of the forward's staging batch, so cuts are
+// batch boundaries.
+#ifndef SEG_SHIFT
+#define SEG_SHIFT 9  // log2 of the segment length; tuning hook (build_ext.py B2R_NVCC_EXTRA).  Measured on C4 (five-render training
+                     // frames/s in flight | scene-view backward alone | human-view backward alone): 256: 2005 | 111 us | 60 us,
+                     // 512: 2101 | 91 us | 63 us, 1024: 2136 | 86 us | 97 us -- every work item pays ~6 dependent global loads
+                     // before its first batch, so fewer, longer items win until the longest chain becomes the tail
+#endif
+constexpr int SEG = 1 << SEG_SHIFT;
 constexpr int CK_PLANE0 = TILE_PIX * 4;              // floats: per pixel (T, C_r, C_g, C_b)
 constexpr int CK_REC_FLOATS = TILE_PIX * 4 + TILE_PIX * 2;  // + per pixel (depth sum, alpha sum)
 constexpr size_t CK_REC_BYTES = (size_t)CK_REC_FLOATS * 4;  // 6144
 // slots of Ctx::classes (written by tile_scan_kernel; positions refer to tile_order, which is sorted longest first)
 enum { CLS_N_LARGE = 0,   // tiles with >= 2048 entries (sorted in chunks)
        CLS_N_GE512 = 1,   // tiles with >= 512 entries  (CTA-class sort; "heavy" tiles of the forward composite)
-       CLS_N_MULTI = 2,   // tiles cut into segments (>= 256 entries), 0 when the caller gave no checkpoint buffer
+       CLS_N_MULTI = 2,   // tiles cut into segments (>= SEG entries), 0 when the caller gave no checkpoint buffer
        CLS_N_CHUNKS = 3,  // sort chunks of the large tiles
        CLS_TOTAL_SEGS = 4,  // segments of the multi-segment tiles
        CLS_N_GE1024 = 5,    // tiles with >= 1024 entries

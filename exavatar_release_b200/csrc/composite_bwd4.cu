@@ -1,4 +1,4 @@
-// composite_bwd4.cu -- K5: backward alpha-composite (App. A.4), one work item per (quarter tile, 256-entry segment).
+// composite_bwd4.cu -- K5: backward alpha-composite (App. A.4), one work item per (quarter tile, 512-entry segment).
 //
 // Replaces the reference rasteriser's backward render kernel.  The per-hit machinery is
 // round 1's composite_bwd3 (64-thread CTA per 8x8 quarter tile, cp.async staging, 8x4 sub-tile cull with a compacted
@@ -7,7 +7,7 @@
 // (splat, warp); scalar colour recurrence; one MUFU.RCP for 1/(1-alpha)).  What changed: the list is no longer walked
 // by one CTA from its last contributor to its first.  The backward recurrences can be ENTERED at any list position p
 // once the state there is known -- T(p), and the colour composited behind p,  (C_final - C_prefix(p)) / T(p) -- and
-// the forward (composite_fwd4.cu) stores exactly that, per pixel, at every 256-entry cut of a list.  So every
+// the forward (composite_fwd4.cu) stores exactly that, per pixel, at every 512-entry cut of a list.  So every
 // (quarter tile, segment) is an independent CTA: the longest serial chain drops from ~1200 hits to <= ~170, the eight
 // CTAs that used to run alone for the last third of the kernel disappear, and no combine pass is needed because the
 // per-Gaussian sums are accumulated atomically anyway.  Error of the subtraction: <= 1 ulp of C (~1e-7) entering
@@ -342,7 +342,7 @@ __device__ __forceinline__ void bwd4_item(const B2RScene& sc, const Ctx& cx, con
 
 // The number of work items -- 4 quarter tiles x (segments of the multi-segment tiles + one per remaining tile) -- is only
 // known on the device, so the grid is a fixed number of CTAs that stride over the items (heaviest first: the item order
-// follows cx.tile_order).  A grid sized for the host-side worst case (capacity / 256 segments) would be mostly CTAs that
+// follows cx.tile_order).  A grid sized for the host-side worst case (capacity / SEG segments) would be mostly CTAs that
 // read two counters and exit -- 185 000 of 191 000 with a generously sized workspace (profiles/r02_notes.md).
 template <bool HAS_DA>
 __global__ void __launch_bounds__(B4_THREADS, B4_MIN_BLOCKS) composite_bwd4_kernel(const B2RScene sc, const Ctx cx,
@@ -369,7 +369,7 @@ __global__ void __launch_bounds__(B4_THREADS, B4_MIN_BLOCKS) composite_bwd4_kern
 
 int launch_composite_bwd(const B2RScene& sc, const Ctx& cx, const B2RBackwardArgs& a, float* gacc, cudaStream_t st) {
   if (!(a.flags & B2R_BWD_SCRATCH_ZEROED)) cudaMemsetAsync(gacc, 0, (size_t)(sc.P > 0 ? sc.P : 1) * 12 * sizeof(float), st);
-  // host-side bound on the item count (every segment beyond a tile's first covers 256 list entries), capped at a few
+  // host-side bound on the item count (every segment beyond a tile's first covers SEG list entries), capped at a few
   // waves of resident CTAs: the kernel strides over the items
   const uint64_t extra = cx.ckpt ? cx.dup_capacity / SEG : 0;
   const uint64_t bound = 4ull * ((uint64_t)cx.tiles + extra);

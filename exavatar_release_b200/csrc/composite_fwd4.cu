@@ -14,9 +14,9 @@
 //   * for every 32 staged splats a warp runs ONE lane-parallel test "can this splat reach alpha >= 1/255 anywhere in my
 //     8x4 rect" (region_max_p2), ballots, and the survivors are appended to a warp-private queue that the hit loop
 //     walks four splats per trip (their exponent evaluations overlap; only the short T recurrence is serial);
-//   * CHECKPOINTS: at every 256-entry cut of a list the per-pixel blend state (T, C, depth sum, alpha sum) is stored
+//   * CHECKPOINTS: at every 512-entry cut of a list the per-pixel blend state (T, C, depth sum, alpha sum) is stored
 //     (when the workspace has room: B2RWorkspace.checkpoints).  Alpha compositing can be re-entered at any list position
-//     once the state there is known, which is what lets composite_bwd4.cu replay every 256-entry segment as an
+//     once the state there is known, which is what lets composite_bwd4.cu replay every 512-entry segment as an
 //     independent work item instead of walking 2000 entries on one warp;
 //   * VIEWS (B2RView): Gaussians outside the view's index range are dropped when a batch is staged (no gather for
 //     them); tiles whose list holds nothing of the view's own (tile_maxid < skip_below) are skipped altogether.
@@ -216,7 +216,7 @@ __global__ void __launch_bounds__(FL_THREADS, F4_MIN_BLOCKS) composite_fwd_kerne
   const uint32_t* ids = cx.dup_ids + range.x;
   const int nb = (n + FL_BATCH - 1) / FL_BATCH;
   const int nrec = (n + SEG - 1) / SEG;
-  float* ck = nullptr;  // checkpoint records of this tile: record j = state at list position min(256 (j+1), n)
+  float* ck = nullptr;  // checkpoint records of this tile: record j = state at list position min(SEG (j+1), n)
   if (cx.ckpt && t_pos < (int)cx.classes[CLS_N_MULTI]) ck = cx.ckpt + (size_t)cx.seg_start[t_pos] * CK_REC_FLOATS;
 
   const uint32_t id_begin = cx.id_begin, id_span = cx.id_span;
@@ -282,7 +282,7 @@ __global__ void __launch_bounds__(FL_THREADS, F4_MIN_BLOCKS) composite_fwd_kerne
       cull_and_blend(stage_raw, half + idx, idx < count, b * FL_BATCH + idx + 1, cw, head, fill, S, rx0, ry0, rx1, ry1, pxf, pyf);
       warp_live = __any_sync(0xffffffffu, alive(S));
     }
-    if (ck && ((b + 1) * FL_BATCH) % SEG == 0 && b + 1 < nb) {  // a cut (multiple of 256): the state must be exact there
+    if (ck && ((b + 1) * FL_BATCH) % SEG == 0 && b + 1 < nb) {  // a cut (multiple of SEG): the state must be exact there
       flush_queue(cw, head, fill, S, pxf, pyf);
       if (inside) store_checkpoint(ck + (size_t)((b + 1) * FL_BATCH / SEG - 1) * CK_REC_FLOATS, pix_in_tile, S);
     }

@@ -269,7 +269,7 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx, const int
     cx.status->reserved[0] = (unsigned long long)bin_cursor[21] | ((unsigned long long)bin_cursor[23] << 32);
     n_large_s = bin_cursor[21];
     // segmented composites: tiles of >= SEG (256) entries are the bins 0..23; cut only when there is room for checkpoints
-    n_multi_s = cx.ckpt ? bin_cursor[24] : 0u;
+    n_multi_s = cx.ckpt ? bin_cursor[32 - SEG_SHIFT] : 0u;  // bins 0..31-s hold n >= 2^s
     cx.classes[CLS_N_LARGE] = bin_cursor[21];
     cx.classes[CLS_N_GE512] = bin_cursor[23];
     cx.classes[CLS_N_GE1024] = bin_cursor[22];
@@ -317,13 +317,13 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx, const int
     }
     return run;
   };
-  static_assert(SORT_CHUNK == 2048 && SEG == 256, "scan_units takes the unit as a shift");
+  static_assert(SORT_CHUNK == 2048 && SEG == (1 << SEG_SHIFT), "scan_units takes the unit as a shift");
   // Tiles of >= 2048 entries are sorted in chunks of SORT_CHUNK by separate CTAs and merged afterwards (binning.cu):
   // chunk_start[t] = first chunk of the t-th tile of tile_order, reserved[1] = number of chunks.
   const uint32_t n_chunks = scan_units(n_large_s, 11, cx.chunk_start);
   // Segment table of the multi-segment tiles (composite_fwd4.cu / composite_bwd4.cu): seg_start[t] = segments of all
   // earlier such tiles = index of the tile's first checkpoint record.
-  uint32_t segs = scan_units(n_multi_s, 8, cx.seg_start);
+  uint32_t segs = scan_units(n_multi_s, SEG_SHIFT, cx.seg_start);
   __syncthreads();
   if (threadIdx.x == 0) {
     cx.status->reserved[1] = n_chunks;

@@ -41,7 +41,7 @@ class FramePlan:
         self.bwd_bytes = self.lib.b2r_backward_scratch_bytes(P)
         # zero once: every backward leaves it zero again (B2R_BWD_SCRATCH_ZEROED), so no memset node per render
         self.bwd_scratch = torch.zeros(self.bwd_bytes, dtype=torch.uint8, device=dev)
-        # segment table + blend-state checkpoints of the forward composite (lets the backward replay 256-entry list
+        # segment table + blend-state checkpoints of the forward composite (lets the backward replay 512-entry list
         # segments as independent work items); `segmented=False` reproduces the round-1 whole-list backward
         segmented = segmented and os.environ.get("B2R_SEGMENTED", "1") != "0"  # A/B switch for measurements
         self.ckpt_bytes = self.lib.b2r_checkpoint_bytes(width, height, self.capacity) if segmented else 0

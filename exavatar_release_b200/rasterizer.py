@@ -161,7 +161,7 @@ def _make_scene(settings: GaussianRasterizationSettings, means3D, shs, colors, o
 
 def _forward_impl(settings, means3D, shs, colors, opac, scales, rots, cov, want_stats=False, skin=None, need_grad=True):
     """need_grad: a backward may follow, so the forward composite also stores its blend-state checkpoints (the segmented
-    backward replays 256-entry list segments independently from them); inference calls skip that buffer."""
+    backward replays 512-entry list segments independently from them); inference calls skip that buffer."""
     lib = L.load()
     dev = means3D.device
     P = int(means3D.shape[0])

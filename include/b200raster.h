@@ -112,8 +112,8 @@ typedef struct B2RWorkspace {
                               duplicate count by polling, without a stream synchronisation */
   uint64_t status_token;   /* caller-chosen, e.g. a call counter */
   /* Optional (ABI v3): room for the segment table + per-pixel blend-state checkpoints the forward composite stores at
-   * every 256-entry cut of a tile's list, >= b2r_checkpoint_bytes(width, height, dup_capacity); saved until backward.
-   * With it the backward composite replays every (quarter tile, 256-entry segment) as an independent work item instead
+   * every 512-entry cut of a tile's list, >= b2r_checkpoint_bytes(width, height, dup_capacity); saved until backward.
+   * With it the backward composite replays every (quarter tile, 512-entry segment) as an independent work item instead
    * of walking a 2000-entry list on one warp.  NULL: lists are not cut (same results, longer serial chains). */
   void* checkpoints;
   size_t checkpoint_bytes;

@@ -48,10 +48,10 @@ def test_size_queries():
     assert lib.b2r_scratch_bytes(1000, 64, 64, 1 << 20) >= 8 << 20
     assert lib.b2r_backward_scratch_bytes(1000) >= 48000
     assert lib.b2r_ctx_bytes(0, 16, 16) > 0
-    # checkpoint store: a segment table + 6 KB per 256-entry cut; grows with the duplicate capacity and the tile count
+    # checkpoint store: a segment table + 6 KB per 512-entry cut; grows with the duplicate capacity and the tile count
     c0 = lib.b2r_checkpoint_bytes(64, 64, 0)
     c1 = lib.b2r_checkpoint_bytes(64, 64, 1 << 20)
-    assert 0 < c0 < c1 and c1 >= (1 << 20) // 256 * 6144
+    assert 0 < c0 < c1 and c1 >= (1 << 20) // 512 * 6144
     assert lib.b2r_checkpoint_bytes(512, 512, 0) > c0
 
 
