@@ -301,7 +301,7 @@ __device__ __forceinline__ void radix_sort_tile(const uint2* src, uint32_t* dst,
 // barriers, 6.6 KB of shared memory per warp, eight tiles per 256-thread CTA.  The CTA-wide version spent most of its
 // time in ~20 barriers per tile with seven of eight warps idle, while holding all 64 warp slots of the SM.
 // ---------------------------------------------------------------------------------------------------------------
-constexpr int WSORT_CAP = 512;
+constexpr int WSORT_CAP = 1 << SORT_CTA_SHIFT;  // warp-class lists are shorter than the CTA-class boundary
 constexpr size_t WSORT_BYTES = (size_t)WSORT_CAP * 12 + 256 * 2;  // keyA, keyB (u32), idxA, idxB (u16), hist (u16)
 
 __device__ __forceinline__ void warp_sort_tile(const uint2* __restrict__ src, uint32_t* __restrict__ dst, const int n,

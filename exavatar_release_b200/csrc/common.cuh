@@ -25,6 +25,9 @@ constexpr float INV_LOG2E = 0.6931471805599453f;
 // that rounding in the per-pixel evaluation can never disagree with a cull decision
 constexpr float CULL_MARGIN2 = 0.02f;
 
+#ifndef SORT_CTA_SHIFT
+#define SORT_CTA_SHIFT 9  // log2 of the shortest list that gets a CTA of its own in the per-tile sort (tuning hook)
+#endif
 constexpr int SORT_CHUNK = 2048;  // per-tile sort: lists are sorted in chunks of this many entries (binning.cu)
 // Segmented composites (composite_fwd4.cu / composite_bwd4.cu).  A tile's depth-sorted list is cut every SEG entries;
 // the forward stores the per-pixel blend state at every cut (a "checkpoint record"), which lets the backward replay

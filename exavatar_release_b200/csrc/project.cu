@@ -265,8 +265,9 @@ __global__ void __launch_bounds__(1024) tile_scan_kernel(const Ctx cx, const int
       bin_cursor[b] = run;
       run += c;
     }
-    // class boundaries of the per-tile sort (binning.cu): bins 0..20 hold n >= 2048, bins 0..22 hold n >= 512
-    cx.status->reserved[0] = (unsigned long long)bin_cursor[21] | ((unsigned long long)bin_cursor[23] << 32);
+    // class boundaries of the per-tile sort (binning.cu): bins 0..20 hold n >= 2048 (sorted in chunks), bins 0..31-s hold
+    // n >= 2^s = SORT_CTA_MIN (one CTA per list; shorter lists are sorted eight to a CTA, one per warp)
+    cx.status->reserved[0] = (unsigned long long)bin_cursor[21] | ((unsigned long long)bin_cursor[32 - SORT_CTA_SHIFT] << 32);
     n_large_s = bin_cursor[21];
     // segmented composites: tiles of >= SEG (256) entries are the bins 0..23; cut only when there is room for checkpoints
     n_multi_s = cx.ckpt ? bin_cursor[32 - SEG_SHIFT] : 0u;  // bins 0..31-s hold n >= 2^s

@@ -74,7 +74,7 @@ def main():
     lib = plan.lib
     tiles = ((W + 15) // 16) * ((H + 15) // 16)
     tf = torch.zeros(tiles * 4, 4, dtype=torch.int64, device=dev)
-    tb = torch.zeros(tiles * 4, 4, dtype=torch.int64, device=dev)
+    tb = torch.zeros(max(tiles * 4, 65536), 4, dtype=torch.int64, device=dev)  # the backward grid strides over its items: one row per CTA (its last item)
     ts = torch.zeros(tiles * 4, 4, dtype=torch.int64, device=dev)
     for fn, t in (("b2r_debug_trace_fwd", tf), ("b2r_debug_trace_bwd", tb), ("b2r_debug_trace_sort", ts)):
         f = getattr(lib, fn)
