@@ -29,11 +29,19 @@ def main():
                     help="with --fused: raster settings built ahead of the loop (a data-loader worker), so the frame has no "
                          "camera D2H synchronisation")
     ap.add_argument("--graph", action="store_true", help="with --fused: TrainingFrameRenderer(use_graph=True)")
+    ap.add_argument("--single", action="store_true", help="one render per frame of the whole workload (e.g. --workload C2)")
+    ap.add_argument("--same-camera", action="store_true", help="reuse one camera tensor set (the per-camera cache hits)")
     a = ap.parse_args()
     wl = WORKLOADS[a.workload]
     dev = torch.device("cuda:0")
     H, W = wl.height, wl.width
-    scene, human, refined = make_population_assets(a.workload, seed=0, device=dev)
+    if a.single:
+        from exavatar_release_b200.synthetic import make_assets
+        whole = make_assets(a.workload, seed=0, device=dev)
+        scene = human = refined = whole
+    else:
+        scene, human, refined = make_population_assets(a.workload, seed=0, device=dev)
+    cam0 = look_at_cam_param(-20.0, (H, W), device=dev)
     bg_r = torch.tensor([0.3, 0.7, 0.2], device=dev)
     tgt = torch.rand(3, H, W, device=dev)
     R = GaussianRenderer()
@@ -52,7 +60,11 @@ def main():
                                GaussianRasterizationSettings) for j in range(8)]
 
     def frame(i):
-        cam = look_at_cam_param(-20.0 + (i % 8) * 5.0, (H, W), device=dev)  # a new camera tensor set every frame
+        cam = cam0 if a.same_camera else look_at_cam_param(-20.0 + (i % 8) * 5.0, (H, W), device=dev)  # new tensors per frame
+        if a.single:
+            lv1 = {k: v.detach().requires_grad_() for k, v in whole.items()}
+            torch.nn.functional.l1_loss(R(lv1, (H, W), cam)["img"], tgt).backward()
+            return
         lv = {n: {k: v.detach().requires_grad_() for k, v in s.items()} for n, s in
               (("scene", scene), ("human", human), ("refined", refined))}
         if fused is not None:
