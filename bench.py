@@ -74,6 +74,7 @@ def parse():
     ap.add_argument("--no-graph", action="store_true", help="do not capture the step in a CUDA graph")
     ap.add_argument("--no-graph-collectives", action="store_true", help="N > 1: issue the all-reduces after the graph replay")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--e2e-lanes", type=int, default=None, help="five pattern: frames in flight on the autograd path of the e2e legs")
     ap.add_argument("--no-eager", action="store_true", help="skip the e2e_eager leg")
     ap.add_argument("--no-single", action="store_true", help="five pattern: skip the extra C2 single-render key")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -684,60 +685,83 @@ def e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_
     h2d = nbytes(host) + F * 3 * N * 4
     d2h = nbytes(host_grads) + F * 4
     renderer = GaussianRenderer()
-    S = max(1, min(4, F))  # frames in flight on the autograd path (each frame: five renders in sequence on its lane)
+    # frames in flight on the autograd path (each frame: five renders in sequence on its lane)
+    # measured on C4 (e2e | e2e_merged): 4 lanes 960 | 1312, 6: 957 | 1228, 8: 997 | 1249 training frames/s
+    S = max(1, min(args.e2e_lanes if args.e2e_lanes else 8, F))        # five-call legs (graph and eager)
+    S_fused = max(1, min(args.e2e_lanes if args.e2e_lanes else 4, F))  # one fused call per frame keeps ~6 kernels in flight itself
     cat = lambda a, b: {k: torch.cat((a[k].detach(), b[k])) for k in a}  # model.py:117-125
 
     fused = []  # one TrainingFrameRenderer per lane (built lazily for the e2e_merged leg)
 
-    def frame_loss_fused(lv, f, tgt, lane):
+    def frame_loss_fused(lv, f, tgt, lane, wait_set):
+        wait_set("human"); wait_set("refined")  # one call renders all five: it needs every set
         out = fused[lane](lv["scene"], lv["human"], lv["refined"], cams[f], bg_r, raster_settings=st_w[f],
                           raster_settings_human=st_r[f])
         imgs = [out[r]["img"] for r in FIVE]
+        wait_set("target")
         return sum(torch.nn.functional.l1_loss(im, tgt) for im in imgs), imgs
 
-    def frame_loss(lv, f, tgt, use_cached_settings):
+    def frame_loss(lv, f, tgt, use_cached_settings, wait_set):
         kw_w = {"raster_settings": st_w[f]} if use_cached_settings else {}
         kw_r = {"raster_settings": st_r[f]} if use_cached_settings else {}
         shape = (H, Wd)
-        imgs = [renderer(lv["scene"], shape, cams[f], **kw_w)["img"],
-                renderer(lv["human"], shape, cams[f], bg_r, **kw_r)["img"],
-                renderer(cat(lv["scene"], lv["human"]), shape, cams[f], **kw_w)["img"],
-                renderer(lv["refined"], shape, cams[f], bg_r, **kw_r)["img"],
-                renderer(cat(lv["scene"], lv["refined"]), shape, cams[f], **kw_w)["img"]]
+        imgs = [renderer(lv["scene"], shape, cams[f], **kw_w)["img"]]
+        wait_set("human")
+        imgs += [renderer(lv["human"], shape, cams[f], bg_r, **kw_r)["img"],
+                 renderer(cat(lv["scene"], lv["human"]), shape, cams[f], **kw_w)["img"]]
+        wait_set("refined")
+        imgs += [renderer(lv["refined"], shape, cams[f], bg_r, **kw_r)["img"],
+                 renderer(cat(lv["scene"], lv["refined"]), shape, cams[f], **kw_w)["img"]]
+        wait_set("target")
         return sum(torch.nn.functional.l1_loss(im, tgt) for im in imgs), imgs
 
     keep_alive = []
     h2d_s, d2h_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    lane_s = [torch.cuda.Stream(dev) for _ in range(S)]
+    lane_s_all = [torch.cuda.Stream(dev) for _ in range(S)]
 
     def body(use_cached_settings=True, use_fused=False):
         cur = torch.cuda.current_stream(dev)
+        S = S_fused if use_fused else len(lane_s_all)
+        lane_s = lane_s_all[:S]
         for st_ in lane_s:
             st_.wait_stream(cur)
         d2h_s.wait_stream(cur)
         h2d_s.wait_stream(cur)
         with torch.cuda.stream(h2d_s):
-            params = {n: {k: v.to(dev, non_blocking=True) for k, v in a.items()} for n, a in host.items()}
-            ev_p = torch.cuda.Event()
-            ev_p.record(h2d_s)
-            tgts, ev_t = [], []
-            for f in range(F):
-                tgts.append(host_targets[f].to(dev, non_blocking=True))
-                e = torch.cuda.Event()
-                e.record(h2d_s)
-                ev_t.append(e)
+            # scene first: the frames start on it while the two human sets are still on the wire (each render waits for
+            # the sets it reads, below)
+            params, ev_set = {}, {}
+            tgts, ev_t = [None] * F, [None] * F
+
+            def up_set(n):
+                params[n] = {k: v.to(dev, non_blocking=True) for k, v in host[n].items()}
+                ev_set[n] = torch.cuda.Event()
+                ev_set[n].record(h2d_s)
+
+            def up_tgt(f):
+                tgts[f] = host_targets[f].to(dev, non_blocking=True)
+                ev_t[f] = torch.cuda.Event()
+                ev_t[f].record(h2d_s)
+
+            for n in ("scene", "human", "refined"):
+                up_set(n)
+            for f in range(F):  # the losses come after the fifth render: the targets travel last
+                up_tgt(f)
         keep_alive.append((params, tgts))
         leaves = []
         for st_ in lane_s:
-            st_.wait_event(ev_p)
-            with torch.cuda.stream(st_):
+            st_.wait_event(ev_set["scene"])
+            with torch.cuda.stream(st_):  # views of the uploaded tensors: no kernel runs here
                 leaves.append({n: {k: v.detach().requires_grad_() for k, v in a.items()} for n, a in params.items()})
+        need = {}  # per lane: has this lane's stream waited for the set yet?
         losses = []
         for f in range(F):
             fs, lv = lane_s[f % S], leaves[f % S]
             with torch.cuda.stream(fs):
-                fs.wait_event(ev_t[f])
-                loss, imgs = frame_loss_fused(lv, f, tgts[f], f % S) if use_fused else frame_loss(lv, f, tgts[f], use_cached_settings)
+                wait_set = lambda n, fs=fs, lane=f % S, f=f: (fs.wait_event(ev_t[f]) if n == "target" else
+                                                               need.setdefault((lane, n), fs.wait_event(ev_set[n]) or True))
+                loss, imgs = (frame_loss_fused(lv, f, tgts[f], f % S, wait_set) if use_fused
+                              else frame_loss(lv, f, tgts[f], use_cached_settings, wait_set))
                 loss.backward()
                 losses.append(loss.detach().reshape(1))
                 keep_alive.append((imgs, loss))
@@ -817,7 +841,7 @@ def e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_
     merged = None
     try:
         from exavatar_release_b200 import TrainingFrameRenderer
-        for _ in range(S):
+        for _ in range(S_fused):
             fused.append(TrainingFrameRenderer(wl.n_scene, wl.n_avatar, (H, Wd), dev, caps_merged))
         side = torch.cuda.Stream(dev)
         side.wait_stream(torch.cuda.current_stream(dev))
@@ -850,7 +874,7 @@ def e2e_five(env, args, wl, wl_key, cams, st_w, st_r, scene_a, human_a, refined_
         if any(fr.overflowed() for fr in fused):
             raise RuntimeError("fixed duplicate capacity overflowed")
         merged = {"value": world * F * ke / (ms_m * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                  "steps": ke, "lanes": S,
+                  "steps": ke, "lanes": S_fused,
                   "api": "TrainingFrameRenderer (exavatar_release_b200/fused.py): the five renders of model.py:117-162 as one "
                          "autograd call per frame (two merged projection+binning passes, five views), same losses, copies "
                          "and graph capture as `e2e`; needs the caller to replace model.py:117-162 (INTEGRATION.md)"}
@@ -1013,7 +1037,7 @@ def bench_single(env, args, wl, wl_key, brief=False):
         host_img = torch.empty(3, H, Wd).pin_memory()
         RZ.set_fixed_capacity(cap)
         h2d_s, d2h_s = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-        lane_s = [torch.cuda.Stream(dev) for _ in range(S)] if S > 1 else None
+        lane_s_all = [torch.cuda.Stream(dev) for _ in range(S)] if S > 1 else None
         keep_alive = []  # nothing allocated inside the capture may be recycled across the forked streams
 
         def upload(f, cur):
