@@ -209,53 +209,102 @@ __device__ __forceinline__ float region_max_p2(float sx, float sy, float A2, flo
   return best;
 }
 
-// Warp-cooperative enumeration of the tiles a Gaussian keeps (rect minus culled tiles).  Every lane brings one
-// Gaussian (or active = false).  Rects of <= KEPT_SMALL tiles are walked by their own lane; larger rects are broadcast
-// and walked by all 32 lanes together, so one 144-tile scene splat no longer stalls 31 idle lanes behind it.  Must be
-// called by full warps.
-constexpr int KEPT_SMALL = 4;
-#ifndef WALK_COOP_COST_N
-#define WALK_COOP_COST_N 70  // tuning hook (build_ext.py B2R_NVCC_EXTRA); 0 = always cooperative above KEPT_SMALL
-#endif
-constexpr unsigned WALK_PRIVATE_COST = 45u, WALK_COOP_COST = WALK_COOP_COST_N;  // instructions per tile / per 32-tile round
+// ---------------------------------------------------------------------------------------------------------------
+// Tile culling by ROWS.  The tiles a splat keeps are those whose pixel-centre rectangle intersects the ellipse
+// E = { p2(d) >= thr2 }.  Round 1 / 2 tested every tile of the 3-sigma rect with region_max_p2 (~45 instructions per tile,
+// and a warp pays the largest rect among its lanes: the projection spent ~45 % of its instructions there).  For one tile
+// ROW the kept tiles form an interval: the band y in [y0, y1] cuts E in a convex set whose x-extent [xl, xr] has a closed
+// form -- the right end of the chord at height dy,  dx(dy) = (-B2 dy - sqrt(D dy^2 + 4 A2 thr2)) / (2 A2)  with
+// D = B2^2 - 4 A2 C2 < 0, is concave in dy, so its maximum over the band is at the clamped apex
+// dy* = -B2 dx_top / (2 C2), dx_top = sqrt(4 C2 thr2 / -D); the left end is its mirror image -- and a tile of the row is
+// kept iff its pixel-centre range meets [xl, xr].  Same set as the per-tile test (the rect spans the whole band, so
+// "rect meets E" <=> "x-range of the rect meets the x-extent of E in the band"), ~40 instructions per row instead of ~45
+// per tile.  The interval is padded by 0.01 px against the rounding of the closed form (a superset is always allowed:
+// the composites cull again per 8x4 pixel rect); a numpy restatement checked it on 2.7 M (splat, tile) pairs: no kept tile
+// missed, 0.03 % more pairs (tests/test_tile_rows.py).
+// ---------------------------------------------------------------------------------------------------------------
+struct RowCull {  // per-splat constants of the row test
+  float sx, sy, A2, B2, nD4, fA4t, dy_ext, dys, inv2A;
+  int mode;       // 0: closed form, 1: keep every tile (culling off / degenerate conic), 2: keep none
+};
+__device__ __forceinline__ RowCull row_cull_setup(float sx, float sy, float A2, float B2, float C2, float thr2, bool no_cull) {
+  RowCull rc;
+  rc.sx = sx; rc.sy = sy; rc.A2 = A2; rc.B2 = B2;
+  rc.mode = (no_cull || thr2 == -INFINITY) ? 1 : 0;
+  const float D = B2 * B2 - 4.f * A2 * C2;      // < 0 for a concave conic
+  const float k = __fdividef(4.f * thr2, -D);   // dy_ext^2 = A2 k, dx_top^2 = C2 k  (A2, C2 < 0 and thr2 < 0 => both > 0)
+  rc.dy_ext = sqrtf(A2 * k);                    // NaN when thr2 > 0 or +inf: the splat reaches 1/255 nowhere
+  const float dx_top = sqrtf(C2 * k);
+  rc.dys = __fdividef(-B2, 2.f * C2) * dx_top;  // dy at the rightmost point of the ellipse
+  rc.nD4 = D;
+  rc.fA4t = 4.f * A2 * thr2;
+  rc.inv2A = __fdividef(1.f, 2.f * A2);
+  if (rc.mode == 0 && !(rc.dy_ext >= 0.f)) rc.mode = 2;
+  return rc;
+}
+constexpr float ROW_PAD = 0.01f;
+// Kept tile columns [tlo, thi] (inclusive; empty when tlo > thi) of tile row `ty` inside the rect columns [x0, x1).
+__device__ __forceinline__ void row_kept_columns(const RowCull& rc, int ty, int x0, int x1, int W, int H, int& tlo, int& thi) {
+  tlo = x0; thi = x1 - 1;
+  if (rc.mode == 1) return;
+  if (rc.mode == 2) { thi = tlo - 1; return; }
+  const float y0 = (float)(ty * TILE), y1 = fminf(y0 + (float)(TILE - 1), (float)(H - 1));
+  const float lo = fmaxf(rc.sy - y1, -rc.dy_ext), hi = fminf(rc.sy - y0, rc.dy_ext);
+  if (!(lo <= hi)) { thi = tlo - 1; return; }
+  const float dyr = fminf(fmaxf(rc.dys, lo), hi), dyl = fminf(fmaxf(-rc.dys, lo), hi);
+  const float disc_r = fmaxf(rc.nD4 * dyr * dyr + rc.fA4t, 0.f), disc_l = fmaxf(rc.nD4 * dyl * dyl + rc.fA4t, 0.f);
+  const float dx_hi = (-rc.B2 * dyr - sqrtf(disc_r)) * rc.inv2A;  // largest dx = centre - x  => smallest x
+  const float dx_lo = (-rc.B2 * dyl + sqrtf(disc_l)) * rc.inv2A;
+  const float xl = rc.sx - dx_hi - ROW_PAD, xr = rc.sx - dx_lo + ROW_PAD;
+  if (!(xl <= (float)(W - 1))) { thi = tlo - 1; return; }  // every tile's last pixel centre is <= W - 1
+  // tile tx spans pixel centres [16 tx, min(16 tx + 15, W - 1)]: kept iff xl <= its last and xr >= its first centre
+  tlo = max(x0, (int)ceilf((xl - (float)(TILE - 1)) * (1.f / TILE)));
+  thi = min(x1 - 1, (int)floorf(xr * (1.f / TILE)));
+}
 
 // tile index t (row-major inside a rect of width w) -> row; exact for the sizes that occur: (t + 0.5) / w is at least
 // 0.5 / w away from an integer, far more than the rounding of the reciprocal and the product
 __device__ __forceinline__ int rect_row(int t, float inv_w) { return (int)(((float)t + 0.5f) * inv_w); }
 
+// Warp-cooperative enumeration of the tiles a Gaussian keeps (rect minus culled tiles).  Every lane brings one
+// Gaussian (or active = false).  A lane walks the rows of its own rect, or -- when few lanes carry tall rects -- a rect is
+// broadcast and its rows are spread over the 32 lanes.  Must be called by full warps.
+constexpr int KEPT_SMALL = 4;
+#ifndef WALK_ROW_COST_N
+#define WALK_ROW_COST_N 40  // tuning hooks (build_ext.py B2R_NVCC_EXTRA): modelled instructions per row / per kept tile
+#endif
+constexpr unsigned WALK_ROW_COST = WALK_ROW_COST_N, WALK_TILE_COST = 10u, WALK_BCAST_COST = 30u;
+
+// bits [pos, pos + cnt) of a 32-bit mask (cnt >= 1, pos + cnt <= 32)
+__device__ __forceinline__ uint32_t bit_run(int pos, int cnt) { return (cnt >= 32 ? 0xffffffffu : ((1u << cnt) - 1u)) << pos; }
+
 // The counting walk (projection): table[ty * gx + tx] += 1 once per kept tile.  Returns, to the owner lane, the KEPT MASK
-// of a rect of at most 32 tiles (bit t = tile t in row-major order); the scatter replays it instead of repeating the
-// region tests.
+// of a rect of at most 32 tiles (bit t = tile t in row-major order); the scatter replays it instead of repeating the walk.
 __device__ __forceinline__ uint32_t warp_count_kept_tiles(bool active, int x0, int y0, int x1, int y1, float px, float py,
                                                           float A2, float B2, float C2, float thr2, bool no_cull, int W,
                                                           int H, int gx, uint32_t* table) {
   const int lane = threadIdx.x & 31;
-  const int w = x1 - x0;
-  const int area = active ? w * (y1 - y0) : 0;
-  auto keep_tile = [&](int tx, int ty, float sx, float sy, float a2, float b2, float c2, float th) {
-    if (no_cull) return true;
-    const float rx0 = (float)(tx * TILE), ry0 = (float)(ty * TILE);
-    const float rx1 = fminf(rx0 + (float)(TILE - 1), (float)(W - 1));
-    const float ry1 = fminf(ry0 + (float)(TILE - 1), (float)(H - 1));
-    return !(region_max_p2(sx, sy, a2, b2, c2, rx0, ry0, rx1, ry1) < th);
-  };
+  const int w = x1 - x0, h = y1 - y0;
+  const int area = active ? w * h : 0;
   uint32_t kept = 0u;
-  // Schedule (warp-uniform): a lane walks its own rect (a region test per tile, ~45 instructions), or the rect is broadcast
-  // and the 32 lanes test 32 of its tiles at once (~70 instructions per round).  One large splat among small ones is
-  // cheaper shared; a warp of scene splats that all cover dozens of tiles is cheaper lane-private (32 rounds of 70 against
-  // max(area) rounds of 45).  The pairs are the same either way.
+  // Schedule (warp-uniform), by modelled cost: every lane walks its own rect (the warp pays the most expensive lane), or
+  // the rects of more than KEPT_SMALL tiles are broadcast one after the other and their rows spread over the lanes.
   const bool big = area > KEPT_SMALL;
-  const unsigned coop_rounds = __reduce_add_sync(0xffffffffu, big ? (unsigned)((area + 31) >> 5) : 0u);
-  const unsigned max_area = __reduce_max_sync(0xffffffffu, (unsigned)area);
-  const bool all_private = max_area * WALK_PRIVATE_COST <= coop_rounds * WALK_COOP_COST + 64u;
+  const unsigned own_cost = area ? (unsigned)h * WALK_ROW_COST + (unsigned)area * WALK_TILE_COST : 0u;
+  const unsigned coop_cost = big ? WALK_BCAST_COST + (unsigned)((h + 31) >> 5) * (WALK_ROW_COST + (unsigned)w * WALK_TILE_COST) : 0u;
+  const unsigned max_own = __reduce_max_sync(0xffffffffu, own_cost);
+  const unsigned sum_coop = __reduce_add_sync(0xffffffffu, coop_cost);
+  const bool all_private = max_own <= sum_coop + 64u;
   if (area > 0 && (all_private || !big)) {
-    int tx = x0, ty = y0;
-    for (int t = 0; t < area; t++) {
-      if (keep_tile(tx, ty, px, py, A2, B2, C2, thr2)) {
-        if (t < 32) kept |= 1u << t;
-        atomicAdd(table + ty * gx + tx, 1u);
+    const RowCull rc = row_cull_setup(px, py, A2, B2, C2, thr2, no_cull);
+    for (int ty = y0; ty < y1; ty++) {
+      int tlo, thi;
+      row_kept_columns(rc, ty, x0, x1, W, H, tlo, thi);
+      if (tlo <= thi) {
+        if (area <= 32) kept |= bit_run((ty - y0) * w + (tlo - x0), thi - tlo + 1);
+        uint32_t* row = table + ty * gx;
+        for (int tx = tlo; tx <= thi; tx++) atomicAdd(row + tx, 1u);
       }
-      if (++tx == x1) { tx = x0; ty++; }
     }
   }
   unsigned mask = all_private ? 0u : __ballot_sync(0xffffffffu, big);
@@ -263,42 +312,43 @@ __device__ __forceinline__ uint32_t warp_count_kept_tiles(bool active, int x0, i
     const int src = __ffs(mask) - 1;
     mask &= mask - 1;
     const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
-    const int bw = __shfl_sync(0xffffffffu, w, src), barea = __shfl_sync(0xffffffffu, area, src);
+    const int bx1 = __shfl_sync(0xffffffffu, x1, src), by1 = __shfl_sync(0xffffffffu, y1, src);
     const float spx = __shfl_sync(0xffffffffu, px, src), spy = __shfl_sync(0xffffffffu, py, src);
     const float sA = __shfl_sync(0xffffffffu, A2, src), sB = __shfl_sync(0xffffffffu, B2, src);
     const float sC = __shfl_sync(0xffffffffu, C2, src), sT = __shfl_sync(0xffffffffu, thr2, src);
-    const float inv_w = __frcp_rn((float)bw);
-    bool k = false;
-    if (lane < barea) {
-      const int r = rect_row(lane, inv_w);
-      const int ty = by0 + r, tx = bx0 + lane - r * bw;
-      k = keep_tile(tx, ty, spx, spy, sA, sB, sC, sT);
-      if (k) atomicAdd(table + ty * gx + tx, 1u);
+    const RowCull rc = row_cull_setup(spx, spy, sA, sB, sC, sT, no_cull);
+    const int bw = bx1 - bx0;
+    const bool small = bw * (by1 - by0) <= 32;
+    uint32_t bits = 0u;
+    for (int ty = by0 + lane; ty < by1; ty += 32) {
+      int tlo, thi;
+      row_kept_columns(rc, ty, bx0, bx1, W, H, tlo, thi);
+      if (tlo <= thi) {
+        if (small) bits |= bit_run((ty - by0) * bw + (tlo - bx0), thi - tlo + 1);
+        uint32_t* row = table + ty * gx;
+        for (int tx = tlo; tx <= thi; tx++) atomicAdd(row + tx, 1u);
+      }
     }
-    const unsigned first = __ballot_sync(0xffffffffu, k);
-    if (lane == src && barea <= 32) kept = first;
-    for (int t = lane + 32; t < barea; t += 32) {
-      const int r = rect_row(t, inv_w);
-      const int ty = by0 + r, tx = bx0 + t - r * bw;
-      if (keep_tile(tx, ty, spx, spy, sA, sB, sC, sT)) atomicAdd(table + ty * gx + tx, 1u);
-    }
+    bits = __reduce_or_sync(0xffffffffu, bits);
+    if (lane == src) kept = bits;
   }
   return kept;
 }
 
 // The replay (scatter): the same (splat, tile) pairs as warp_count_kept_tiles produced.  Per pair: old = table[tile]++,
 // then post(old, tile, u0, u1) with the owner's two payload words.  A rect of <= 32 tiles is replayed by its own lane from
-// the stored mask (a loop over the set bits: no shuffles, no region test; the warp pays the largest pair count among its
-// lanes, a handful).  Larger rects are walked by the 32 lanes together with the region test, so px..thr2 need to be valid
-// on lanes whose rect has more than 32 tiles only.  Must be called by full warps.
+// the stored mask (a loop over the set bits: no shuffles, no geometry; the warp pays the largest pair count among its
+// lanes, a handful).  Larger rects repeat the row walk (the same row_kept_columns on the same inputs in a unit compiled
+// with the same flags, so the pairs are identical), privately or with their rows spread over the lanes; px..thr2 need to
+// be valid on lanes whose rect has more than 32 tiles only.  Must be called by full warps.
 template <typename F>
 __device__ __forceinline__ void warp_replay_kept_tiles(bool active, int x0, int y0, int x1, int y1, uint32_t kept, float px,
                                                        float py, float A2, float B2, float C2, float thr2, uint32_t u0,
                                                        uint32_t u1, bool no_cull, int W, int H, int gx, uint32_t* table,
                                                        F&& post) {
   const int lane = threadIdx.x & 31;
-  const int w = x1 - x0;
-  const int area = active ? w * (y1 - y0) : 0;
+  const int w = x1 - x0, h = y1 - y0;
+  const int area = active ? w * h : 0;
   if (area > 0 && area <= 32) {
     const float inv_w = __frcp_rn((float)w);
     const int tile0 = y0 * gx + x0;
@@ -310,25 +360,21 @@ __device__ __forceinline__ void warp_replay_kept_tiles(bool active, int x0, int 
     }
   }
   const bool big = area > 32;
-  const unsigned coop_rounds = __reduce_add_sync(0xffffffffu, big ? (unsigned)((area + 31) >> 5) : 0u);
-  if (coop_rounds == 0u) return;
-  auto keep_tile = [&](int tx, int ty, float sx, float sy, float a2, float b2, float c2, float th) {
-    if (no_cull) return true;
-    const float rx0 = (float)(tx * TILE), ry0 = (float)(ty * TILE);
-    const float rx1 = fminf(rx0 + (float)(TILE - 1), (float)(W - 1));
-    const float ry1 = fminf(ry0 + (float)(TILE - 1), (float)(H - 1));
-    return !(region_max_p2(sx, sy, a2, b2, c2, rx0, ry0, rx1, ry1) < th);
-  };
-  const unsigned max_area = __reduce_max_sync(0xffffffffu, big ? (unsigned)area : 0u);
-  if (max_area * WALK_PRIVATE_COST <= coop_rounds * WALK_COOP_COST) {  // see warp_count_kept_tiles
+  const unsigned own_cost = big ? (unsigned)h * WALK_ROW_COST + (unsigned)area * WALK_TILE_COST : 0u;
+  const unsigned coop_cost = big ? WALK_BCAST_COST + (unsigned)((h + 31) >> 5) * (WALK_ROW_COST + (unsigned)w * WALK_TILE_COST) : 0u;
+  const unsigned sum_coop = __reduce_add_sync(0xffffffffu, coop_cost);
+  if (sum_coop == 0u) return;
+  const unsigned max_own = __reduce_max_sync(0xffffffffu, own_cost);
+  if (max_own <= sum_coop) {
     if (big) {
-      int tx = x0, ty = y0;
-      for (int t = 0; t < area; t++) {
-        if (keep_tile(tx, ty, px, py, A2, B2, C2, thr2)) {
+      const RowCull rc = row_cull_setup(px, py, A2, B2, C2, thr2, no_cull);
+      for (int ty = y0; ty < y1; ty++) {
+        int tlo, thi;
+        row_kept_columns(rc, ty, x0, x1, W, H, tlo, thi);
+        for (int tx = tlo; tx <= thi; tx++) {
           const int tile = ty * gx + tx;
           post(atomicAdd(table + tile, 1u), tile, u0, u1);
         }
-        if (++tx == x1) { tx = x0; ty++; }
       }
     }
     return;
@@ -338,16 +384,16 @@ __device__ __forceinline__ void warp_replay_kept_tiles(bool active, int x0, int 
     const int src = __ffs(mask) - 1;
     mask &= mask - 1;
     const int bx0 = __shfl_sync(0xffffffffu, x0, src), by0 = __shfl_sync(0xffffffffu, y0, src);
-    const int bw = __shfl_sync(0xffffffffu, w, src), barea = __shfl_sync(0xffffffffu, area, src);
+    const int bx1 = __shfl_sync(0xffffffffu, x1, src), by1 = __shfl_sync(0xffffffffu, y1, src);
     const uint32_t s0 = __shfl_sync(0xffffffffu, u0, src), s1 = __shfl_sync(0xffffffffu, u1, src);
-    const float inv_w = __frcp_rn((float)bw);
     const float spx = __shfl_sync(0xffffffffu, px, src), spy = __shfl_sync(0xffffffffu, py, src);
     const float sA = __shfl_sync(0xffffffffu, A2, src), sB = __shfl_sync(0xffffffffu, B2, src);
     const float sC = __shfl_sync(0xffffffffu, C2, src), sT = __shfl_sync(0xffffffffu, thr2, src);
-    for (int t = lane; t < barea; t += 32) {
-      const int r = rect_row(t, inv_w);
-      const int ty = by0 + r, tx = bx0 + t - r * bw;
-      if (keep_tile(tx, ty, spx, spy, sA, sB, sC, sT)) {
+    const RowCull rc = row_cull_setup(spx, spy, sA, sB, sC, sT, no_cull);
+    for (int ty = by0 + lane; ty < by1; ty += 32) {
+      int tlo, thi;
+      row_kept_columns(rc, ty, bx0, bx1, W, H, tlo, thi);
+      for (int tx = tlo; tx <= thi; tx++) {
         const int tile = ty * gx + tx;
         post(atomicAdd(table + tile, 1u), tile, s0, s1);
       }
